@@ -1,0 +1,389 @@
+// C-ABI of libhf_b200.so (include/hf_b200.h): plan lifetime, workspace, thin entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "hf_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void hf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out, cudaStream_t st);
+int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const double* init,
+                  int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
+                  int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
+                  int32_t* niter, cudaStream_t st);
+int hf_sample_toys_launch(hf_plan* plan, const double* pars, uint64_t seed, uint64_t offset,
+                          int64_t N, double* out, cudaStream_t st);
+
+extern "C" {
+
+int hf_version(void) { return 100; }
+const char* hf_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------ plan
+namespace {
+struct Packer {
+    // lays out every table in one device allocation, 256-byte aligned
+    std::vector<char> host;
+    size_t add(const void* src, size_t bytes) {
+        size_t off = (host.size() + 255) / 256 * 256;
+        host.resize(off + bytes, 0);
+        if (src && bytes) memcpy(host.data() + off, src, bytes);
+        return off;
+    }
+};
+}  // namespace
+
+int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
+    if (!d || !out) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    if (d->n_pars <= 0 || d->n_bins <= 0 || d->n_samples <= 0 || d->n_segs <= 0 || d->n_hs < 0 ||
+        d->n_sf < 0 || d->n_bf_slots < 0 || d->n_gauss < 0 || d->n_pois < 0 || d->n_aux < 0 ||
+        (d->n_hs > 0 && d->n_hs_rows <= 0)) {
+        hf_set_error("inconsistent plan sizes");
+        return HF_ERR_INVALID;
+    }
+    const int P = d->n_pars, NB = d->n_bins, S = d->n_samples, NSEG = d->n_segs, H = d->n_hs,
+              R = d->n_hs ? d->n_hs_rows : 0, NSF = d->n_sf, K = d->n_bf_slots;
+    // ---- validate indices on the host (a bad plan must not become an illegal address)
+    auto in_range = [](const int32_t* a, size_t n, int lo, int hi) {
+        for (size_t i = 0; i < n; ++i)
+            if (a[i] < lo || a[i] >= hi) return false;
+        return true;
+    };
+    bool ok = in_range(d->bin_seg, NB, 0, NSEG) && in_range(d->hs_par, H, 0, P) &&
+              in_range(d->hs_row_sample, R, 0, S) && in_range(d->sf_par, NSF, 0, P) &&
+              in_range(d->sf_kind, NSF, 0, 3) && in_range(d->bf_par, (size_t)K * S * NB, -1, P) &&
+              in_range(d->g_par, d->n_gauss, 0, P) && in_range(d->g_aux, d->n_gauss, 0, std::max(d->n_aux, 1)) &&
+              in_range(d->p_par, d->n_pois, 0, P) && in_range(d->p_aux, d->n_pois, 0, std::max(d->n_aux, 1));
+    if (ok) {
+        if (d->sf_ptr[0] != 0 || d->sf_ptr[S * NSEG] != NSF) ok = false;
+        for (int q = 0; ok && q < S * NSEG; ++q)
+            if (d->sf_ptr[q + 1] < d->sf_ptr[q]) ok = false;
+    }
+    if (d->hs_code != HF_HS_CODE0 && d->hs_code != HF_HS_CODE4P) ok = false;
+    if (!ok) {
+        hf_set_error("plan tables hold out-of-range indices");
+        return HF_ERR_INVALID;
+    }
+
+    hf_plan* plan = new (std::nothrow) hf_plan();
+    if (!plan) return HF_ERR_NOMEM;
+    DevPlan& dp = plan->d;
+    memset(&dp, 0, sizeof(dp));
+    dp.P = P; dp.NB = NB; dp.S = S; dp.NAUX = d->n_aux; dp.NSEG = NSEG; dp.H = H; dp.R = R;
+    dp.hs_code = d->hs_code; dp.NSF = NSF; dp.K = K; dp.NG = d->n_gauss; dp.NPO = d->n_pois;
+    dp.D = NB + d->n_aux;
+    dp.Hp = (H + 31) / 32 * 32;
+    dp.has_clip_sample = d->has_clip_sample; dp.has_clip_bin = d->has_clip_bin;
+    dp.clip_sample = d->clip_sample; dp.clip_bin = d->clip_bin;
+    plan->P = P; plan->NB = NB; plan->S = S; plan->NAUX = d->n_aux; plan->NSEG = NSEG; plan->H = H;
+    plan->R = R; plan->NSF = NSF; plan->K = K; plan->NG = d->n_gauss; plan->NPO = d->n_pois;
+    plan->D = dp.D;
+
+    // derived host tables
+    std::vector<int32_t> sample_row(S, -1);
+    for (int r = 0; r < R; ++r) sample_row[d->hs_row_sample[r]] = r;
+    // transposed histosys tables [R][NB][Hp]
+    const size_t ncell = (size_t)R * NB;
+    std::vector<double> t1t(ncell * dp.Hp, 0.0), t2t(ncell * dp.Hp, 0.0);
+    for (int h = 0; h < H; ++h)
+        for (size_t c = 0; c < ncell; ++c) {
+            t1t[c * dp.Hp + h] = d->hs_t1[(size_t)h * ncell + c];
+            t2t[c * dp.Hp + h] = d->hs_t2[(size_t)h * ncell + c];
+        }
+    // by-parameter CSR of the scalar-factor entries
+    std::vector<int32_t> sfp_ptr(P + 1, 0), sfp_entry(NSF), sfp_q(NSF);
+    for (int e = 0; e < NSF; ++e) sfp_ptr[d->sf_par[e] + 1]++;
+    for (int p = 0; p < P; ++p) sfp_ptr[p + 1] += sfp_ptr[p];
+    {
+        std::vector<int32_t> fill(sfp_ptr.begin(), sfp_ptr.end() - 1);
+        for (int q = 0; q < S * NSEG; ++q)
+            for (int e = d->sf_ptr[q]; e < d->sf_ptr[q + 1]; ++e) {
+                const int k = fill[d->sf_par[e]]++;
+                sfp_entry[k] = e;
+                sfp_q[k] = q;
+            }
+    }
+    std::vector<int32_t> cons_kind(P, 0), cons_idx(P, 0);
+    for (int i = 0; i < d->n_gauss; ++i) { cons_kind[d->g_par[i]] = 1; cons_idx[d->g_par[i]] = i; }
+    for (int i = 0; i < d->n_pois; ++i) { cons_kind[d->p_par[i]] = 2; cons_idx[d->p_par[i]] = i; }
+
+    Packer pk;
+    const size_t o_nom = pk.add(d->nominal, sizeof(double) * S * NB);
+    const size_t o_seg = pk.add(d->bin_seg, sizeof(int32_t) * NB);
+    const size_t o_hpar = pk.add(d->hs_par, sizeof(int32_t) * H);
+    const size_t o_hrow = pk.add(d->hs_row_sample, sizeof(int32_t) * R);
+    const size_t o_srow = pk.add(sample_row.data(), sizeof(int32_t) * S);
+    const size_t o_t1 = pk.add(d->hs_t1, sizeof(double) * H * ncell);
+    const size_t o_t2 = pk.add(d->hs_t2, sizeof(double) * H * ncell);
+    const size_t o_t1t = pk.add(t1t.data(), sizeof(double) * t1t.size());
+    const size_t o_t2t = pk.add(t2t.data(), sizeof(double) * t2t.size());
+    const size_t o_sfptr = pk.add(d->sf_ptr, sizeof(int32_t) * (S * NSEG + 1));
+    const size_t o_sfpar = pk.add(d->sf_par, sizeof(int32_t) * NSF);
+    const size_t o_sfkind = pk.add(d->sf_kind, sizeof(int32_t) * NSF);
+    const size_t o_sfcoef = pk.add(d->sf_coef, sizeof(double) * 8 * NSF);
+    const size_t o_sfpptr = pk.add(sfp_ptr.data(), sizeof(int32_t) * (P + 1));
+    const size_t o_sfpent = pk.add(sfp_entry.data(), sizeof(int32_t) * NSF);
+    const size_t o_sfpq = pk.add(sfp_q.data(), sizeof(int32_t) * NSF);
+    const size_t o_bf = pk.add(d->bf_par, sizeof(int32_t) * (size_t)K * S * NB);
+    const size_t o_gpar = pk.add(d->g_par, sizeof(int32_t) * d->n_gauss);
+    const size_t o_gaux = pk.add(d->g_aux, sizeof(int32_t) * d->n_gauss);
+    const size_t o_gsig = pk.add(d->g_sigma, sizeof(double) * d->n_gauss);
+    const size_t o_ppar = pk.add(d->p_par, sizeof(int32_t) * d->n_pois);
+    const size_t o_paux = pk.add(d->p_aux, sizeof(int32_t) * d->n_pois);
+    const size_t o_pfac = pk.add(d->p_factor, sizeof(double) * d->n_pois);
+    const size_t o_ck = pk.add(cons_kind.data(), sizeof(int32_t) * P);
+    const size_t o_ci = pk.add(cons_idx.data(), sizeof(int32_t) * P);
+    pk.add(nullptr, 256);
+
+    cudaError_t e = cudaMalloc(&plan->table_block, pk.host.size());
+    if (e != cudaSuccess) {
+        hf_set_error("cudaMalloc(%zu) for plan tables: %s", pk.host.size(), cudaGetErrorString(e));
+        delete plan;
+        return HF_ERR_NOMEM;
+    }
+    e = cudaMemcpy(plan->table_block, pk.host.data(), pk.host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        hf_set_error("cudaMemcpy plan tables: %s", cudaGetErrorString(e));
+        cudaFree(plan->table_block);
+        delete plan;
+        return HF_ERR_CUDA;
+    }
+    char* base = (char*)plan->table_block;
+#define DP(T, off) reinterpret_cast<const T*>(base + (off))
+    dp.nominal = DP(double, o_nom); dp.bin_seg = DP(int, o_seg); dp.hs_par = DP(int, o_hpar);
+    dp.hs_row_sample = DP(int, o_hrow); dp.sample_hs_row = DP(int, o_srow);
+    dp.t1 = DP(double, o_t1); dp.t2 = DP(double, o_t2); dp.t1t = DP(double, o_t1t);
+    dp.t2t = DP(double, o_t2t); dp.sf_ptr = DP(int, o_sfptr); dp.sf_par = DP(int, o_sfpar);
+    dp.sf_kind = DP(int, o_sfkind); dp.sf_coef = DP(double, o_sfcoef);
+    dp.sfp_ptr = DP(int, o_sfpptr); dp.sfp_entry = DP(int, o_sfpent); dp.sfp_q = DP(int, o_sfpq);
+    dp.bf_par = DP(int, o_bf); dp.g_par = DP(int, o_gpar); dp.g_aux = DP(int, o_gaux);
+    dp.g_sigma = DP(double, o_gsig); dp.p_par = DP(int, o_ppar); dp.p_aux = DP(int, o_paux);
+    dp.p_factor = DP(double, o_pfac); dp.par_cons_kind = DP(int, o_ck); dp.par_cons_idx = DP(int, o_ci);
+#undef DP
+    cudaGetDevice(&plan->device);
+    cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device);
+    *out = plan;
+    return HF_OK;
+}
+
+void hf_plan_destroy(hf_plan* plan) {
+    if (!plan) return;
+    cudaFree(plan->table_block);
+    cudaFree(plan->work_block);
+    cudaFree(plan->dconst);
+    cudaFree(plan->fit_block);
+    cudaFree(plan->stage_block);
+    delete plan;
+}
+
+int64_t hf_plan_launch_count(const hf_plan* plan) { return plan ? plan->launches : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ workspace
+int hf_ensure_work(hf_plan* plan, int64_t ld, int64_t data_rows) {
+    const DevPlan& pl = plan->d;
+    if (ld > plan->work_ld) {
+        if (plan->work_block) cudaFree(plan->work_block);
+        plan->work_block = nullptr;
+        plan->work_ld = 0;
+        const int64_t nq = (int64_t)pl.S * pl.NSEG;
+        // [parsT P][c1,c2,dc1,dc2 4H][Fseg,Gseg 2nq][gradT P][mainv 1]
+        const int64_t rows = 2LL * pl.P + 4LL * pl.H + 2 * nq + 1;
+        const size_t bytes = sizeof(double) * (size_t)rows * (size_t)ld + 256;
+        cudaError_t e = cudaMalloc(&plan->work_block, bytes);
+        if (e != cudaSuccess) {
+            hf_set_error("cudaMalloc(%zu) for the evaluation workspace: %s", bytes, cudaGetErrorString(e));
+            return HF_ERR_NOMEM;
+        }
+        plan->work_ld = ld;
+    }
+    {
+        // carve for the ld of THIS call (leading dimension = ld so padded tiles stay in range)
+        const int64_t nq = (int64_t)pl.S * pl.NSEG;
+        double* p = (double*)plan->work_block;
+        Work& w = plan->w;
+        w.parsT = p; p += (int64_t)pl.P * ld;
+        w.c1T = p; p += (int64_t)pl.H * ld;
+        w.c2T = p; p += (int64_t)pl.H * ld;
+        w.dc1T = p; p += (int64_t)pl.H * ld;
+        w.dc2T = p; p += (int64_t)pl.H * ld;
+        w.FsegT = p; p += nq * ld;
+        w.GsegT = p; p += nq * ld;
+        w.gradT = p; p += (int64_t)pl.P * ld;
+        w.mainv = p;
+    }
+    if (data_rows > plan->dconst_cap) {
+        if (plan->dconst) cudaFree(plan->dconst);
+        plan->dconst = nullptr;
+        plan->dconst_cap = 0;
+        cudaError_t e = cudaMalloc(&plan->dconst, sizeof(double) * (size_t)data_rows);
+        if (e != cudaSuccess) {
+            hf_set_error("cudaMalloc for data constants: %s", cudaGetErrorString(e));
+            return HF_ERR_NOMEM;
+        }
+        plan->dconst_cap = data_rows;
+    }
+    plan->w.dconst = plan->dconst;
+    return HF_OK;
+}
+
+static int ensure_stage(hf_plan* plan, size_t bytes) {
+    if (bytes <= plan->stage_bytes) return HF_OK;
+    if (plan->stage_block) cudaFree(plan->stage_block);
+    plan->stage_block = nullptr;
+    plan->stage_bytes = 0;
+    cudaError_t e = cudaMalloc(&plan->stage_block, bytes);
+    if (e != cudaSuccess) {
+        hf_set_error("cudaMalloc(%zu) for host-call staging: %s", bytes, cudaGetErrorString(e));
+        return HF_ERR_NOMEM;
+    }
+    plan->stage_bytes = bytes;
+    return HF_OK;
+}
+
+extern "C" {
+
+int hf_logpdf(hf_plan* plan, const double* pars, const double* data, int64_t data_rows, int64_t B,
+              double* out, void* stream) {
+    if (!plan || !pars || !data || !out) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    return hf_eval_launch(plan, pars, data, data_rows, B, out, nullptr, (cudaStream_t)stream);
+}
+
+int hf_logpdf_grad(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
+                   int64_t B, double* out, double* grad, void* stream) {
+    if (!plan || !pars || !data || !out || !grad) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    return hf_eval_launch(plan, pars, data, data_rows, B, out, grad, (cudaStream_t)stream);
+}
+
+int hf_expected_data(hf_plan* plan, const double* pars, int64_t B, double* out, void* stream) {
+    if (!plan || !pars || !out) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    return hf_expected_launch(plan, pars, B, out, (cudaStream_t)stream);
+}
+
+int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* data_host,
+                        int64_t data_rows, int64_t B, double* out_host, double* grad_host,
+                        void* stream) {
+    if (!plan || !pars_host || !data_host || !out_host) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t P = plan->P, D = plan->D;
+    const size_t n_pars = (size_t)B * P, n_data = (size_t)data_rows * D;
+    const size_t bytes = sizeof(double) * (n_pars + n_data + (size_t)B + (grad_host ? n_pars : 0)) + 1024;
+    int rc = ensure_stage(plan, bytes);
+    if (rc) return rc;
+    double* d_pars = (double*)plan->stage_block;
+    double* d_data = d_pars + n_pars;
+    double* d_out = d_data + n_data;
+    double* d_grad = grad_host ? d_out + B : nullptr;
+    HF_CUDA_OK(cudaMemcpyAsync(d_pars, pars_host, sizeof(double) * n_pars, cudaMemcpyHostToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * n_data, cudaMemcpyHostToDevice, st));
+    rc = hf_eval_launch(plan, d_pars, d_data, data_rows, B, d_out, d_grad, st);
+    if (rc) return rc;
+    HF_CUDA_OK(cudaMemcpyAsync(out_host, d_out, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (grad_host)
+        HF_CUDA_OK(cudaMemcpyAsync(grad_host, d_grad, sizeof(double) * n_pars, cudaMemcpyDeviceToHost, st));
+    HF_CUDA_OK(cudaStreamSynchronize(st));
+    return HF_OK;
+}
+
+void hf_fit_default_opts(hf_fit_opts* o) {
+    if (!o) return;
+    o->max_iter = 200;
+    o->history = 8;
+    o->tol_edm = 1e-11;
+    o->tol_step = 1e-8;
+    o->verbose = 0;
+    o->reserved = 0;
+}
+
+int hf_fit_batch(hf_plan* plan, const double* data, int64_t data_rows, const double* init,
+                 int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
+                 int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
+                 int32_t* niter, void* stream) {
+    if (!plan || !data || !init || !lo || !hi || !fixed || !x || !fun || !status) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    return hf_fit_launch(plan, data, data_rows, init, init_rows, lo, hi, fixed, N, opts, x, fun,
+                         status, niter, (cudaStream_t)stream);
+}
+
+int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,
+                      const double* init_host, int64_t init_rows, const double* lo_host,
+                      const double* hi_host, const uint8_t* fixed_host, int64_t N,
+                      const hf_fit_opts* opts, double* x_host, double* fun_host,
+                      int32_t* status_host, int32_t* niter_host, void* stream) {
+    if (!plan || !data_host || !init_host || !lo_host || !hi_host || !fixed_host || !x_host ||
+        !fun_host || !status_host) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t P = plan->P, D = plan->D;
+    const size_t nd = (size_t)data_rows * D, ni = (size_t)init_rows * P, nx = (size_t)N * P;
+    const size_t bytes = sizeof(double) * (nd + ni + 2 * P + nx + N) + sizeof(int32_t) * 2 * N + P + 4096;
+    int rc = ensure_stage(plan, bytes);
+    if (rc) return rc;
+    double* d_data = (double*)plan->stage_block;
+    double* d_init = d_data + nd;
+    double* d_lo = d_init + ni;
+    double* d_hi = d_lo + P;
+    double* d_x = d_hi + P;
+    double* d_fun = d_x + nx;
+    int32_t* d_status = (int32_t*)(d_fun + N);
+    int32_t* d_niter = d_status + N;
+    uint8_t* d_fixed = (uint8_t*)(d_niter + N);
+    HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * nd, cudaMemcpyHostToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(d_init, init_host, sizeof(double) * ni, cudaMemcpyHostToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(d_lo, lo_host, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(d_hi, hi_host, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(d_fixed, fixed_host, P, cudaMemcpyHostToDevice, st));
+    rc = hf_fit_launch(plan, d_data, data_rows, d_init, init_rows, d_lo, d_hi, d_fixed, N, opts, d_x,
+                       d_fun, d_status, d_niter, st);
+    if (rc) return rc;
+    HF_CUDA_OK(cudaMemcpyAsync(x_host, d_x, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
+    HF_CUDA_OK(cudaMemcpyAsync(fun_host, d_fun, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    HF_CUDA_OK(cudaMemcpyAsync(status_host, d_status, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    if (niter_host)
+        HF_CUDA_OK(cudaMemcpyAsync(niter_host, d_niter, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    HF_CUDA_OK(cudaStreamSynchronize(st));
+    return HF_OK;
+}
+
+int hf_sample_toys(hf_plan* plan, const double* pars, uint64_t seed, uint64_t offset, int64_t N,
+                   double* out, void* stream) {
+    if (!plan || !pars || !out) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    return hf_sample_toys_launch(plan, pars, seed, offset, N, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,626 @@
+// K1 / K2: fused HistFactory log-likelihood (and analytic gradient) for a batch of parameter
+// points.  sm_100a, fp64 vector pipe (no tensor cores: see DESIGN.md).
+//
+// Pipeline per batch (all on one stream):
+//   hf_prep_kernel      per (point, parameter) transposition to batch-major + histosys
+//                       coefficients c1,c2,dc1,dc2 + per-(sample,segment) scalar-factor products
+//   hf_main_kernel      the hot kernel: one CTA per PT parameter points x all bins.
+//                         forward : thread = bin, register tile acc[RC rows][PT points], histosys
+//                                   tables streamed coalesced from L2 ([H][R][NB]), per-point
+//                                   coefficients broadcast from shared memory; sample sum,
+//                                   Poisson main term, warp-shuffle reduction over bins
+//                         backward: thread = histosys modifier, w*F tile staged in shared memory,
+//                                   transposed tables ([R][NB][H]) streamed coalesced
+//   hf_finish_kernel    scalar-factor / constraint gradient pieces, constraint terms, constants,
+//                       transposition back to row-major [B][P]
+//
+// Reference being replaced: pdf.py:645-713, modifiers/*.py apply(), interpolators/code{0,1,4,4p}.py,
+// constraints.py:100-141,219-262, tensor/numpy_backend.py:435-436,482-490, probability.py:276-299.
+#include <math.h>
+#include <stdio.h>
+
+#include "hf_internal.cuh"
+
+// ------------------------------------------------------------------------------------------
+// prep: grid-stride over points; lanes = consecutive points so batch-major stores coalesce.
+// ------------------------------------------------------------------------------------------
+__global__ void hf_transpose_pars_kernel(DevPlan pl, Work w, const double* __restrict__ pars,
+                                         int64_t B, int64_t ld) {
+    // tile transpose [B][P] -> [P][ld]; padded points replicate point B-1
+    __shared__ double tile[32][33];
+    const int64_t pt0 = (int64_t)blockIdx.x * 32;
+    const int p0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        int64_t pt = pt0 + j;
+        if (pt >= B) pt = B - 1;
+        const int p = p0 + tx;
+        tile[j][tx] = (p < pl.P) ? pars[pt * pl.P + p] : 0.0;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j;
+        const int64_t pt = pt0 + tx;
+        if (p < pl.P && pt < ld) w.parsT[(int64_t)p * ld + pt] = tile[tx][j];
+    }
+}
+
+__global__ void hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
+    const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= ld) return;
+    // blockIdx.y strides over the work items: first H histosys modifiers, then S*NSEG products
+    const int nq = pl.S * pl.NSEG;
+    for (int item = blockIdx.y; item < pl.H + nq; item += gridDim.y) {
+        if (item < pl.H) {
+            const int h = item;
+            const double a = w.parsT[(int64_t)pl.hs_par[h] * ld + pt];
+            double c1, c2, d1, d2;
+            hf_hs_coeffs(pl.hs_code, a, c1, c2, d1, d2);
+            w.c1T[(int64_t)h * ld + pt] = c1;
+            w.c2T[(int64_t)h * ld + pt] = c2;
+            if (do_grad) {
+                w.dc1T[(int64_t)h * ld + pt] = d1;
+                w.dc2T[(int64_t)h * ld + pt] = d2;
+            }
+        } else {
+            const int q = item - pl.H;
+            double prod = 1.0;
+            const int e1 = pl.sf_ptr[q + 1];
+            for (int e = pl.sf_ptr[q]; e < e1; ++e) {
+                const double t = w.parsT[(int64_t)pl.sf_par[e] * ld + pt];
+                double f, dl;
+                hf_sf_eval(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, t, f, dl);
+                prod *= f;
+            }
+            w.FsegT[(int64_t)q * ld + pt] = prod;
+        }
+    }
+}
+
+// theta-independent terms of one data row:  - sum_b lgamma(n_b+1) - sum_pois lgamma(a+1)
+//                                           - sum_gauss ln(sigma sqrt(2 pi))
+__global__ void hf_data_const_kernel(DevPlan pl, const double* __restrict__ data, int64_t rows,
+                                     double* __restrict__ out) {
+    const int64_t row = blockIdx.x;
+    if (row >= rows) return;
+    const double* d = data + row * pl.D;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < pl.NB; i += blockDim.x) acc -= lgamma(d[i] + 1.0);
+    for (int i = threadIdx.x; i < pl.NPO; i += blockDim.x) acc -= lgamma(d[pl.NB + pl.p_aux[i]] + 1.0);
+    for (int i = threadIdx.x; i < pl.NG; i += blockDim.x)
+        acc -= log(pl.g_sigma[i] * 2.5066282746310002);  // sqrt(2 pi), numpy_backend.py:486-488
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) out[row] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the hot kernel
+// ------------------------------------------------------------------------------------------
+// F = Fseg[s][seg] (scalar factors) and bf = product of per-bin factors of cell (s, bb)
+template <int PT>
+__device__ __forceinline__ void load_fseg(const DevPlan& pl, const Work& w, int64_t ld,
+                                          int64_t pt0, int s, int seg, double (&F)[PT]) {
+    const double2* fp =
+        reinterpret_cast<const double2*>(w.FsegT + ((int64_t)s * pl.NSEG + seg) * ld + pt0);
+#pragma unroll
+    for (int i = 0; i < PT / 2; ++i) {
+        const double2 v = fp[i];
+        F[2 * i] = v.x;
+        F[2 * i + 1] = v.y;
+    }
+}
+
+template <int PT>
+__device__ __forceinline__ void mul_binfactors(const DevPlan& pl, const Work& w, int64_t ld,
+                                               int64_t pt0, int s, int bb, double (&F)[PT]) {
+    for (int k = 0; k < pl.K; ++k) {
+        const int p = pl.bf_par[((int64_t)k * pl.S + s) * pl.NB + bb];
+        if (p >= 0) {
+            const double2* gp = reinterpret_cast<const double2*>(w.parsT + (int64_t)p * ld + pt0);
+#pragma unroll
+            for (int i = 0; i < PT / 2; ++i) {
+                const double2 v = gp[i];
+                F[2 * i] *= v.x;
+                F[2 * i + 1] *= v.y;
+            }
+        }
+    }
+}
+
+template <int PT>
+__device__ __forceinline__ void load_factor(const DevPlan& pl, const Work& w, int64_t ld,
+                                            int64_t pt0, int s, int bb, int seg,
+                                            double (&F)[PT]) {
+    load_fseg<PT>(pl, w, ld, pt0, s, seg, F);
+    mul_binfactors<PT>(pl, w, ld, pt0, s, bb, F);
+}
+
+template <int PT, int RC, int TB, bool GRAD>
+__global__ void __launch_bounds__(TB, (PT >= 16) ? 2 : 3)
+hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
+               int64_t data_stride) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int WPAD = PT + 2;  // 16-byte aligned rows, conflict-free vector stores
+    double* c1s = smem;                      // [H][PT]
+    double* c2s = c1s + (int64_t)pl.H * PT;  // [H][PT]
+    double* wfs = c2s + (int64_t)pl.H * PT;  // GRAD: [R*TB][WPAD]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int64_t pt0 = (int64_t)blockIdx.x * PT;
+    const int H = pl.H, R = pl.R, NB = pl.NB, S = pl.S;
+
+    for (int i = tid; i < H * PT; i += TB) {
+        const int h = i / PT, j = i - h * PT;
+        c1s[i] = w.c1T[(int64_t)h * ld + pt0 + j];
+        c2s[i] = w.c2T[(int64_t)h * ld + pt0 + j];
+    }
+    __syncthreads();
+
+    const int ntiles = (NB + TB - 1) / TB;
+    const int64_t hstride = (int64_t)R * NB;
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int b = tile * TB + tid;
+        const bool valid = b < NB;
+        const int bb = valid ? b : NB - 1;
+        const int seg = pl.bin_seg[bb];
+
+        double lam[PT];
+#pragma unroll
+        for (int i = 0; i < PT; ++i) lam[i] = 0.0;
+
+        // ---- (1a) samples that carry histosys: register-tiled contraction over modifiers
+        for (int rc0 = 0; rc0 < R; rc0 += RC) {
+            double acc[RC][PT];
+#pragma unroll
+            for (int j = 0; j < RC; ++j)
+#pragma unroll
+                for (int i = 0; i < PT; ++i) acc[j][i] = 0.0;
+            const double* t1p[RC];
+            const double* t2p[RC];
+#pragma unroll
+            for (int j = 0; j < RC; ++j) {
+                const int row = (rc0 + j < R) ? rc0 + j : R - 1;
+                t1p[j] = pl.t1 + (int64_t)row * NB + bb;
+                t2p[j] = pl.t2 + (int64_t)row * NB + bb;
+            }
+#pragma unroll 2
+            for (int h = 0; h < H; ++h) {
+                double t1v[RC], t2v[RC];
+#pragma unroll
+                for (int j = 0; j < RC; ++j) {
+                    t1v[j] = __ldg(t1p[j] + h * hstride);
+                    t2v[j] = __ldg(t2p[j] + h * hstride);
+                }
+                const double2* a2 = reinterpret_cast<const double2*>(c1s + h * PT);
+                const double2* g2 = reinterpret_cast<const double2*>(c2s + h * PT);
+#pragma unroll
+                for (int i = 0; i < PT / 2; ++i) {
+                    const double2 a = a2[i];
+                    const double2 g = g2[i];
+#pragma unroll
+                    for (int j = 0; j < RC; ++j) {
+                        acc[j][2 * i] = fma(a.x, t1v[j], fma(g.x, t2v[j], acc[j][2 * i]));
+                        acc[j][2 * i + 1] = fma(a.y, t1v[j], fma(g.y, t2v[j], acc[j][2 * i + 1]));
+                    }
+                }
+            }
+            // fold the chunk into lambda; stash base = nominal + delta for the backward sweep
+#pragma unroll
+            for (int j = 0; j < RC; ++j) {
+                const int row = rc0 + j;
+                if (row < R) {
+                    const int s = pl.hs_row_sample[row];
+                    const double nom = pl.nominal[(int64_t)s * NB + bb];
+                    double F[PT];
+                    load_factor<PT>(pl, w, ld, pt0, s, bb, seg, F);
+#pragma unroll
+                    for (int i = 0; i < PT; ++i) {
+                        const double base = nom + acc[j][i];
+                        double r = F[i] * base;
+                        if (pl.has_clip_sample) r = fmax(r, pl.clip_sample);
+                        lam[i] += r;
+                        if (GRAD) wfs[((int64_t)row * TB + tid) * WPAD + i] = base;
+                    }
+                }
+            }
+        }
+        // ---- (1b) samples without histosys
+        for (int s = 0; s < S; ++s) {
+            if (pl.sample_hs_row[s] >= 0) continue;
+            const double nom = pl.nominal[(int64_t)s * NB + bb];
+            double F[PT];
+            load_factor<PT>(pl, w, ld, pt0, s, bb, seg, F);
+#pragma unroll
+            for (int i = 0; i < PT; ++i) {
+                double r = F[i] * nom;
+                if (pl.has_clip_sample) r = fmax(r, pl.clip_sample);
+                lam[i] += r;
+            }
+        }
+
+        // ---- (2) Poisson main term + d/dlambda
+        double wgt[PT];
+        {
+            double term[PT];
+#pragma unroll
+            for (int i = 0; i < PT; ++i) {
+                int64_t pt = pt0 + i;
+                if (pt >= B) pt = B - 1;
+                const double n = data[pt * data_stride + bb];
+                double l = lam[i];
+                bool live = true;
+                if (pl.has_clip_bin && l < pl.clip_bin) {
+                    l = pl.clip_bin;
+                    live = false;
+                }
+                term[i] = valid ? hf_pois_term(n, l) : 0.0;
+                wgt[i] = (valid && live) ? (n / l - 1.0) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < PT; ++i) {
+                double v = term[i];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (lane == 0) atomicAdd(&w.mainv[pt0 + i], v);
+            }
+        }
+
+        if (GRAD) {
+            // ---- (3) w*F per cell for the backward sweep; G_{s,seg}; per-bin factor gradients
+            const int seg0 = __shfl_sync(0xffffffffu, seg, 0);
+            const bool uniform = __all_sync(0xffffffffu, seg == seg0);
+            for (int s = 0; s < S; ++s) {
+                const int row = pl.sample_hs_row[s];
+                const double nom = pl.nominal[(int64_t)s * NB + bb];
+                // wr0 = w * (prod of per-bin factors) * base  : G_{s,seg} excludes the scalar
+                // factors so that d/dtheta of a normfactor stays finite at theta == 0
+                double wr0[PT], wr[PT];
+#pragma unroll
+                for (int i = 0; i < PT; ++i) wr0[i] = 1.0;
+                mul_binfactors<PT>(pl, w, ld, pt0, s, bb, wr0);
+                {
+                    double F[PT];
+                    load_fseg<PT>(pl, w, ld, pt0, s, seg, F);
+#pragma unroll
+                    for (int i = 0; i < PT; ++i) {
+                        const double base =
+                            (row >= 0) ? wfs[((int64_t)row * TB + tid) * WPAD + i] : nom;
+                        const double fb = F[i] * wr0[i];
+                        const double r = fb * base;
+                        const bool live = !(pl.has_clip_sample && r < pl.clip_sample);
+                        const double wl = live ? wgt[i] : 0.0;
+                        wr[i] = wl * r;
+                        wr0[i] = wl * wr0[i] * base;
+                        if (row >= 0) wfs[((int64_t)row * TB + tid) * WPAD + i] = wl * fb;
+                    }
+                }
+                // per-bin factors: d/dgamma = w r / gamma
+                for (int k = 0; k < pl.K; ++k) {
+                    const int p = pl.bf_par[((int64_t)k * S + s) * NB + bb];
+                    if (p >= 0 && valid) {
+#pragma unroll
+                        for (int i = 0; i < PT; ++i) {
+                            const double g = w.parsT[(int64_t)p * ld + pt0 + i];
+                            atomicAdd(&w.gradT[(int64_t)p * ld + pt0 + i], wr[i] / g);
+                        }
+                    }
+                }
+                // G_{s,seg} += w * bf * base  (reduced over the bins of a segment)
+                double* gp = w.GsegT + ((int64_t)s * pl.NSEG + seg) * ld + pt0;
+                if (uniform) {
+#pragma unroll
+                    for (int i = 0; i < PT; ++i) {
+                        double v = wr0[i];
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                        if (lane == 0) atomicAdd(gp + i, v);
+                    }
+                } else if (valid) {
+#pragma unroll
+                    for (int i = 0; i < PT; ++i) atomicAdd(gp + i, wr0[i]);
+                }
+            }
+            __syncthreads();
+
+            // ---- (4) backward sweep: thread = histosys modifier, reduce over the tile's cells
+            //          grad_h += dc1 * sum wF*T1 + dc2 * sum wF*T2
+            const int nb_tile = min(TB, NB - tile * TB);
+            for (int h = tid; h < pl.Hp; h += TB) {
+                double u[PT], v[PT];
+#pragma unroll
+                for (int i = 0; i < PT; ++i) u[i] = v[i] = 0.0;
+                for (int row = 0; row < R; ++row) {
+                    const double* q1 = pl.t1t + ((int64_t)row * NB + tile * TB) * pl.Hp + h;
+                    const double* q2 = pl.t2t + ((int64_t)row * NB + tile * TB) * pl.Hp + h;
+                    const double* wrow = wfs + (int64_t)row * TB * WPAD;
+#pragma unroll 4
+                    for (int c = 0; c < nb_tile; ++c) {
+                        const double a = __ldg(q1 + (int64_t)c * pl.Hp);
+                        const double g = __ldg(q2 + (int64_t)c * pl.Hp);
+                        const double2* wf2 = reinterpret_cast<const double2*>(wrow + c * WPAD);
+#pragma unroll
+                        for (int i = 0; i < PT / 2; ++i) {
+                            const double2 x = wf2[i];
+                            u[2 * i] = fma(x.x, a, u[2 * i]);
+                            u[2 * i + 1] = fma(x.y, a, u[2 * i + 1]);
+                            v[2 * i] = fma(x.x, g, v[2 * i]);
+                            v[2 * i + 1] = fma(x.y, g, v[2 * i + 1]);
+                        }
+                    }
+                }
+                if (h < H) {
+                    const int p = pl.hs_par[h];
+#pragma unroll
+                    for (int i = 0; i < PT; ++i) {
+                        const double d1 = w.dc1T[(int64_t)h * ld + pt0 + i];
+                        const double d2 = w.dc2T[(int64_t)h * ld + pt0 + i];
+                        atomicAdd(&w.gradT[(int64_t)p * ld + pt0 + i], d1 * u[i] + d2 * v[i]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finish: constraints, scalar-factor gradients, constants, transposition to row-major
+// ------------------------------------------------------------------------------------------
+__global__ void hf_finish_value_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
+                                       const double* __restrict__ data, int64_t data_stride,
+                                       int64_t dconst_stride, double* __restrict__ out) {
+    const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= B) return;
+    const double* aux = data + pt * data_stride + pl.NB;
+    double acc = w.mainv[pt] + w.dconst[pt * dconst_stride];
+    for (int i = 0; i < pl.NG; ++i) {
+        const double th = w.parsT[(int64_t)pl.g_par[i] * ld + pt];
+        const double z = (aux[pl.g_aux[i]] - th) / (1.4142135623730951 * pl.g_sigma[i]);
+        acc -= z * z;  // numpy_backend.py:489
+    }
+    for (int i = 0; i < pl.NPO; ++i) {
+        const double th = w.parsT[(int64_t)pl.p_par[i] * ld + pt];
+        acc += hf_pois_term(aux[pl.p_aux[i]], th * pl.p_factor[i]);
+    }
+    out[pt] = acc;
+}
+
+__global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
+                                      const double* __restrict__ data, int64_t data_stride,
+                                      double* __restrict__ grad) {
+    // 32 points x 32 parameters per block; transposed through shared memory so that both the
+    // batch-major reads and the row-major writes coalesce
+    __shared__ double tile[32][33];
+    const int64_t pt0 = (int64_t)blockIdx.x * 32;
+    const int p0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j;
+        const int64_t pt = pt0 + tx;
+        double g = 0.0;
+        if (p < pl.P && pt < B) {
+            g = w.gradT[(int64_t)p * ld + pt];
+            const double th = w.parsT[(int64_t)p * ld + pt];
+            // scalar factors (normsys / normfactor / lumi): sum_e (dF_q/dtheta) * G_q with
+            // dF_q/dtheta = dlog f_e * F_q, or the product of the *other* factors of q for a
+            // plain theta factor (finite at theta == 0: the POI sits on its bound in q~ fits)
+            const int e1 = pl.sfp_ptr[p + 1];
+            for (int k = pl.sfp_ptr[p]; k < e1; ++k) {
+                const int e = pl.sfp_entry[k];
+                const int q = pl.sfp_q[k];
+                double coef;
+                if (pl.sf_kind[e] == HF_SF_THETA) {
+                    coef = 1.0;
+                    for (int e2 = pl.sf_ptr[q]; e2 < pl.sf_ptr[q + 1]; ++e2) {
+                        if (e2 == e) continue;
+                        double f2, dl2;
+                        hf_sf_eval(pl.sf_kind[e2], pl.sf_coef + 8 * (int64_t)e2,
+                                   w.parsT[(int64_t)pl.sf_par[e2] * ld + pt], f2, dl2);
+                        coef *= f2;
+                    }
+                } else {
+                    double f, dl;
+                    hf_sf_eval(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, th, f, dl);
+                    coef = dl * w.FsegT[(int64_t)q * ld + pt];
+                }
+                g = fma(coef, w.GsegT[(int64_t)q * ld + pt], g);
+            }
+            const int ck = pl.par_cons_kind[p];
+            if (ck == 1) {
+                const int i = pl.par_cons_idx[p];
+                const double sg = pl.g_sigma[i];
+                g += (data[pt * data_stride + pl.NB + pl.g_aux[i]] - th) / (sg * sg);
+            } else if (ck == 2) {
+                const int i = pl.par_cons_idx[p];
+                g += data[pt * data_stride + pl.NB + pl.p_aux[i]] / th - pl.p_factor[i];
+            }
+        }
+        tile[j][tx] = g;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t pt = pt0 + j;
+        const int p = p0 + tx;
+        if (p < pl.P && pt < B) grad[pt * pl.P + p] = tile[tx][j];
+    }
+}
+
+// expected data [B][D]: lambda via the forward kernel pieces is overkill for an off-path call;
+// one thread per (point, bin).  Model.expected_data, pdf.py:886-906.
+__global__ void hf_expected_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
+                                   double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * pl.D) return;
+    const int64_t pt = idx / pl.D;
+    const int j = (int)(idx - pt * pl.D);
+    if (j >= pl.NB) {
+        const int a = j - pl.NB;
+        double v = 0.0;
+        for (int i = 0; i < pl.NG; ++i)
+            if (pl.g_aux[i] == a) v = w.parsT[(int64_t)pl.g_par[i] * ld + pt];
+        for (int i = 0; i < pl.NPO; ++i)
+            if (pl.p_aux[i] == a) v = w.parsT[(int64_t)pl.p_par[i] * ld + pt] * pl.p_factor[i];
+        out[idx] = v;
+        return;
+    }
+    const int b = j;
+    const int seg = pl.bin_seg[b];
+    double lam = 0.0;
+    for (int s = 0; s < pl.S; ++s) {
+        double F = w.FsegT[((int64_t)s * pl.NSEG + seg) * ld + pt];
+        for (int k = 0; k < pl.K; ++k) {
+            const int p = pl.bf_par[((int64_t)k * pl.S + s) * pl.NB + b];
+            if (p >= 0) F *= w.parsT[(int64_t)p * ld + pt];
+        }
+        double base = pl.nominal[(int64_t)s * pl.NB + b];
+        const int row = pl.sample_hs_row[s];
+        if (row >= 0) {
+            for (int h = 0; h < pl.H; ++h) {
+                const int64_t o = ((int64_t)h * pl.R + row) * pl.NB + b;
+                base = fma(w.c1T[(int64_t)h * ld + pt], pl.t1[o],
+                           fma(w.c2T[(int64_t)h * ld + pt], pl.t2[o], base));
+            }
+        }
+        double r = F * base;
+        if (pl.has_clip_sample) r = fmax(r, pl.clip_sample);
+        lam += r;
+    }
+    if (pl.has_clip_bin) lam = fmax(lam, pl.clip_bin);
+    out[idx] = lam;
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+template <int PT, int RC, int TB>
+static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data,
+                       int64_t data_stride, bool grad, cudaStream_t st) {
+    const DevPlan& pl = plan->d;
+    size_t smem = sizeof(double) * (size_t)(2 * pl.H * PT);
+    if (grad) smem += sizeof(double) * (size_t)pl.R * TB * (PT + 2);
+    const dim3 grid((unsigned)(ld / PT));
+    if (grad) {
+        auto k = hf_main_kernel<PT, RC, TB, true>;
+        HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, data_stride);
+    } else {
+        auto k = hf_main_kernel<PT, RC, TB, false>;
+        HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, data_stride);
+    }
+    HF_CUDA_OK(cudaGetLastError());
+    plan->launches++;
+    return HF_OK;
+}
+
+// smem budget decides the point tile: PT=16 needs (2H*16 + R*128*18)*8 bytes for the gradient.
+static int pick_pt(const hf_plan* plan, bool grad, int64_t B) {
+    const DevPlan& pl = plan->d;
+    const size_t lim = 200 * 1024;
+    auto need = [&](int pt) {
+        size_t s = sizeof(double) * (size_t)(2 * pl.H * pt);
+        if (grad) s += sizeof(double) * (size_t)pl.R * 128 * (pt + 2);
+        return s;
+    };
+    if (B >= 16 * 148 && need(16) <= lim / 2) return 16;
+    if (B >= 8 * 64 && need(8) <= lim) return 8;
+    if (need(4) <= lim) return 4;
+    if (need(2) <= lim) return 2;
+    return 0;
+}
+
+int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
+                   int64_t B, double* out, double* grad, cudaStream_t st) {
+    if (B <= 0) return HF_OK;
+    const DevPlan& pl = plan->d;
+    if (data_rows != 1 && data_rows != B) {
+        hf_set_error("data_rows must be 1 or B (got %lld, B=%lld)", (long long)data_rows, (long long)B);
+        return HF_ERR_INVALID;
+    }
+    const bool do_grad = grad != nullptr;
+    const int PT = pick_pt(plan, do_grad, B);
+    if (PT == 0) {
+        hf_set_error("model too large for the shared-memory tile (H=%d, R=%d)", pl.H, pl.R);
+        return HF_ERR_UNSUPPORTED;
+    }
+    const int64_t ld = round_up(B, 32);
+    int rc = hf_ensure_work(plan, ld, data_rows);
+    if (rc) return rc;
+    Work& w = plan->w;
+    const int64_t dstride = (data_rows == 1) ? 0 : pl.D;
+
+    {
+        dim3 grid((unsigned)(ld / 32), (unsigned)((pl.P + 31) / 32));
+        hf_transpose_pars_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, pars, B, ld);
+        plan->launches++;
+    }
+    {
+        const int items = pl.H + pl.S * pl.NSEG;
+        int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
+        dim3 grid((unsigned)((ld + 127) / 128), (unsigned)gy);
+        hf_prep_kernel<<<grid, 128, 0, st>>>(pl, w, ld, do_grad ? 1 : 0);
+        plan->launches++;
+    }
+    HF_CUDA_OK(cudaMemsetAsync(w.mainv, 0, sizeof(double) * ld, st));
+    if (do_grad) {
+        HF_CUDA_OK(cudaMemsetAsync(w.gradT, 0, sizeof(double) * ld * pl.P, st));
+        HF_CUDA_OK(cudaMemsetAsync(w.GsegT, 0, sizeof(double) * ld * pl.S * pl.NSEG, st));
+    }
+    hf_data_const_kernel<<<(unsigned)data_rows, 128, 0, st>>>(pl, data, data_rows, plan->dconst);
+    plan->launches++;
+    w.dconst = plan->dconst;
+
+    // point tile: RC = rows per register tile
+    if (PT == 16) {
+        if (pl.R >= 3 || pl.R == 0) rc = launch_main<16, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
+        else if (pl.R == 2) rc = launch_main<16, 2, 128>(plan, B, ld, data, dstride, do_grad, st);
+        else rc = launch_main<16, 1, 128>(plan, B, ld, data, dstride, do_grad, st);
+    } else if (PT == 8) {
+        if (pl.R >= 3 || pl.R == 0) rc = launch_main<8, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
+        else rc = launch_main<8, 2, 128>(plan, B, ld, data, dstride, do_grad, st);
+    } else if (PT == 4) {
+        rc = launch_main<4, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
+    } else {
+        rc = launch_main<2, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
+    }
+    if (rc) return rc;
+
+    hf_finish_value_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(
+        pl, w, B, ld, data, dstride, (data_rows == 1) ? 0 : 1, out);
+    plan->launches++;
+    if (do_grad) {
+        dim3 grid((unsigned)((B + 31) / 32), (unsigned)((pl.P + 31) / 32));
+        hf_finish_grad_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, B, ld, data, dstride, grad);
+        plan->launches++;
+    }
+    HF_CUDA_OK(cudaGetLastError());
+    return HF_OK;
+}
+
+int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out, cudaStream_t st) {
+    if (B <= 0) return HF_OK;
+    const DevPlan& pl = plan->d;
+    const int64_t ld = round_up(B, 32);
+    int rc = hf_ensure_work(plan, ld, 1);
+    if (rc) return rc;
+    Work& w = plan->w;
+    dim3 grid((unsigned)(ld / 32), (unsigned)((pl.P + 31) / 32));
+    hf_transpose_pars_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, pars, B, ld);
+    const int items = pl.H + pl.S * pl.NSEG;
+    int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
+    hf_prep_kernel<<<dim3((unsigned)((ld + 127) / 128), (unsigned)gy), 128, 0, st>>>(pl, w, ld, 0);
+    const int64_t n = B * pl.D;
+    hf_expected_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl, w, B, ld, out);
+    plan->launches += 3;
+    HF_CUDA_OK(cudaGetLastError());
+    return HF_OK;
+}

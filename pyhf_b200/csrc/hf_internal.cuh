@@ -1,0 +1,160 @@
+// Internal definitions shared by the kernels of libhf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hf_b200.h"
+
+#define HF_MAX_PT 16
+
+// Device-resident plan tables (all pointers device memory, immutable after hf_plan_create).
+struct DevPlan {
+    int P, NB, S, NAUX, NSEG, H, R, hs_code, NSF, K, NG, NPO, D, Hp;
+    int has_clip_sample, has_clip_bin;
+    double clip_sample, clip_bin;
+    const double* nominal;       // [S][NB]
+    const int* bin_seg;          // [NB]
+    const int* hs_par;           // [H]
+    const int* hs_row_sample;    // [R]
+    const int* sample_hs_row;    // [S]  (-1: sample carries no histosys)
+    const double* t1;            // [H][R][NB]
+    const double* t2;            // [H][R][NB]
+    const double* t1t;           // [R][NB][Hp]  (h fastest: backward sweep)
+    const double* t2t;           // [R][NB][Hp]
+    const int* sf_ptr;           // [S*NSEG+1]
+    const int* sf_par;           // [NSF]
+    const int* sf_kind;          // [NSF]
+    const double* sf_coef;       // [NSF][8]
+    const int* sfp_ptr;          // [P+1]   by-parameter CSR of scalar-factor entries
+    const int* sfp_entry;        // [NSF]   entry index
+    const int* sfp_q;            // [NSF]   q = sample*NSEG+seg of that entry
+    const int* bf_par;           // [K][S][NB]
+    const int* g_par;            // [NG]
+    const int* g_aux;            // [NG]
+    const double* g_sigma;       // [NG]
+    const int* p_par;            // [NPO]
+    const int* p_aux;            // [NPO]
+    const double* p_factor;      // [NPO]
+    const int* par_cons_kind;    // [P] 0 none, 1 gauss, 2 poisson
+    const int* par_cons_idx;     // [P] index into g_* / p_*
+};
+
+// Per-call scratch, batch-major ("parameter-batch-major": point index fastest) so that warps
+// whose lanes are points read/write coalesced.  ld = padded number of points.
+struct Work {
+    double* parsT;  // [P][ld]
+    double* c1T;    // [H][ld]   histosys coefficient of T1
+    double* c2T;    // [H][ld]   histosys coefficient of T2
+    double* dc1T;   // [H][ld]
+    double* dc2T;   // [H][ld]
+    double* FsegT;  // [S*NSEG][ld]  product of scalar factors per (sample, segment)
+    double* GsegT;  // [S*NSEG][ld]  sum_{b in seg} w_b r_{s,b}
+    double* gradT;  // [P][ld]
+    double* mainv;  // [ld]          main-term partial sums
+    double* dconst; // [data_rows]   -sum lgamma(n+1) - sum ln(sigma sqrt(2pi)) ... (theta-independent)
+};
+
+// ---------------------------------------------------------------- interpolation primitives
+// histosys: delta = c1*T1 + c2*T2.  code4p: interpolators/code4p.py:63-117; code0: code0.py:66-88.
+__host__ __device__ inline void hf_hs_coeffs(int code, double a, double& c1, double& c2,
+                                             double& dc1, double& dc2) {
+    if (code == HF_HS_CODE4P) {
+        c1 = a;
+        dc1 = 1.0;
+        if (a > 1.0) {
+            c2 = 8.0 * a;
+            dc2 = 8.0;
+        } else if (a < -1.0) {
+            c2 = -8.0 * a;
+            dc2 = -8.0;
+        } else {
+            const double a2 = a * a;
+            c2 = a2 * (a2 * (a2 * 3.0 - 10.0) + 15.0);
+            dc2 = a * (a2 * (a2 * 18.0 - 40.0) + 30.0);
+        }
+    } else {
+        const bool pos = a > 0.0;
+        c1 = pos ? a : 0.0;
+        c2 = pos ? 0.0 : a;
+        dc1 = pos ? 1.0 : 0.0;
+        dc2 = pos ? 0.0 : 1.0;
+    }
+}
+
+// scalar factor f(theta) and dlog f/dtheta.  code4: interpolators/code4.py:178-239 (alpha>=1 up,
+// alpha<=-1 down, 6th-order polynomial between); code1: code1.py:84-104 (alpha>0 up).
+__host__ __device__ inline void hf_sf_eval(int kind, const double* __restrict__ cf, double t,
+                                           double& f, double& dl) {
+    if (kind == HF_SF_THETA) {
+        f = t;
+        dl = 1.0 / t;
+        return;
+    }
+    const double lnu = cf[0], lnd = cf[1];
+    if (kind == HF_SF_CODE4 && t > -1.0 && t < 1.0) {
+        double poly = cf[7], dpoly = 0.0;
+#pragma unroll
+        for (int i = 6; i >= 2; --i) {
+            dpoly = dpoly * t + poly;
+            poly = poly * t + cf[i];
+        }
+        dpoly = dpoly * t + poly;
+        poly = poly * t + 1.0;
+        f = poly;
+        dl = dpoly / poly;
+        return;
+    }
+    const bool up = (kind == HF_SF_CODE4) ? (t >= 1.0) : (t > 0.0);
+    if (up) {
+        f = exp(t * lnu);
+        dl = lnu;
+    } else {
+        f = exp(-t * lnd);
+        dl = -lnd;
+    }
+}
+
+// main / constraint Poisson term without the theta-independent lgamma(n+1):
+// xlogy(n, lam) - lam   (tensor/numpy_backend.py:435-436)
+__host__ __device__ inline double hf_pois_term(double n, double lam) {
+    const double xl = (n == 0.0 && !(lam != lam)) ? 0.0 : n * log(lam);
+    return xl - lam;
+}
+
+// ---------------------------------------------------------------- host-side helpers
+void hf_set_error(const char* fmt, ...);
+#define HF_CUDA_OK(call)                                                              \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            hf_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,         \
+                         cudaGetErrorString(e__));                                    \
+            return HF_ERR_CUDA;                                                       \
+        }                                                                             \
+    } while (0)
+
+struct hf_plan {
+    DevPlan d;
+    void* table_block = nullptr;  // one allocation holding every table
+    // workspace
+    Work w;
+    void* work_block = nullptr;
+    int64_t work_ld = 0;       // points capacity
+    int64_t dconst_cap = 0;
+    double* dconst = nullptr;
+    // fit workspace
+    void* fit_block = nullptr;
+    size_t fit_bytes = 0;
+    // staging for the *_host entry points
+    void* stage_block = nullptr;
+    size_t stage_bytes = 0;
+    int64_t launches = 0;
+    int device = 0;
+    int sm_count = 148;
+    // host copies of small tables the host logic needs
+    int P, NB, S, NAUX, NSEG, H, R, NSF, K, NG, NPO, D;
+};
+
+int hf_ensure_work(hf_plan* plan, int64_t B, int64_t data_rows);
+int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
+                   int64_t B, double* out, double* grad, cudaStream_t st);
