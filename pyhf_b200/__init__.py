@@ -1,0 +1,21 @@
+"""pyhf_b200 -- B200-native (sm_100a) hot path for pyhf: batched HistFactory NLL + gradient,
+batched bounded MLE fits and toy sampling behind pyhf's backend / optimizer plugin sockets.
+
+    import pyhf, pyhf_b200
+    pyhf.set_backend(pyhf_b200.b200_backend(), pyhf_b200.b200_optimizer())
+
+Hand-written CUDA in ``libhf_b200.so`` (C-ABI: include/hf_b200.h); no CPU fallback.
+"""
+from .backend import B200Backend, TorchCarrierBackend, b200_backend  # noqa: F401
+from .optimizer import B200Optimizer, b200_optimizer  # noqa: F401
+from .plan import HostPlan, PlanError, extract_plan  # noqa: F401
+
+
+def __getattr__(name):
+    # device-side API is imported lazily so that ``import pyhf_b200`` works on a CPU-only box
+    if name in ("DevicePlan", "plan_for", "qmu_tilde_batch", "toy_hypotest", "FitResult",
+                "teststat", "pvalue_counts", "fp64_peak_tflops"):
+        from . import batched
+
+        return getattr(batched, name)
+    raise AttributeError(name)

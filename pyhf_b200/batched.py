@@ -1,0 +1,339 @@
+"""Explicit batched API over the C-ABI (device tensors in, device tensors out).
+
+pyhf has no call for "evaluate B parameter points" or "fit N datasets" (its ``batch_size`` is a
+build-time property of the model, reference pdf.py:598-600), so the plugin objects
+(``b200_backend`` / ``b200_optimizer``) and users who want the throughput call this module:
+
+    plan = pyhf_b200.plan_for(model)              # compile once per model / device
+    val, grad = plan.logpdf_grad(pars[B, P], data)           # K2
+    res = plan.fit(data[N, D], fixed=mask)                   # K3
+    toys = plan.sample_toys(pars, n=100_000, seed=1)         # K4
+    out = qmu_tilde_batch(plan, 1.0, toys)                   # K3 + K5
+
+torch is only the owner of device memory and of the CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .plan import HostPlan, cached_plan
+
+__all__ = ["DevicePlan", "plan_for", "FitResult", "qmu_tilde_batch", "toy_hypotest",
+           "sample_poisson", "sample_normal", "teststat", "pvalue_counts", "fp64_peak_tflops"]
+
+F64 = torch.float64
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_tensor(x, device, dtype=F64):
+    if isinstance(x, torch.Tensor):
+        t = x.detach()
+        if t.device != device or t.dtype != dtype:
+            t = t.to(device=device, dtype=dtype)
+        return t.contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x)), device=device).to(dtype).contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@dataclass
+class FitResult:
+    x: torch.Tensor        # [N, P] fitted parameters (fixed ones at their given value)
+    fun: torch.Tensor      # [N]    2*NLL at x (all constant terms included, = twice_nll)
+    status: torch.Tensor   # [N]    0 converged / 1 iteration limit / 2 numerical failure
+    niter: torch.Tensor    # [N]
+
+
+class DevicePlan:
+    """A model compiled into device tables (``hf_plan``)."""
+
+    def __init__(self, host: HostPlan, device=None):
+        lib = _lib.require()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyhf_b200 needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.host = host
+        self._keep = []
+        d = _lib.PlanDesc()
+        for k in ("n_pars", "n_bins", "n_samples", "n_aux", "n_segs", "n_hs", "n_hs_rows",
+                  "hs_code", "n_sf", "n_bf_slots", "n_gauss", "n_pois"):
+            setattr(d, k, int(getattr(host, k)))
+        d.has_clip_sample = int(host.has_clip_sample)
+        d.has_clip_bin = int(host.has_clip_bin)
+        d.clip_sample = float(host.clip_sample)
+        d.clip_bin = float(host.clip_bin)
+        for k in ("nominal", "bin_seg", "hs_par", "hs_row_sample", "hs_t1", "hs_t2", "sf_ptr",
+                  "sf_par", "sf_kind", "sf_coef", "bf_par", "g_par", "g_aux", "g_sigma", "p_par",
+                  "p_aux", "p_factor"):
+            arr = np.ascontiguousarray(getattr(host, k))
+            if arr.size == 0:  # keep a valid address for empty tables
+                arr = np.zeros(1, dtype=arr.dtype)
+            self._keep.append(arr)
+            setattr(d, k, arr.ctypes.data)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.hf_plan_create(C.byref(d), C.byref(handle)))
+        self._h = handle
+        self._lib = lib
+        self._finalizer = weakref.finalize(self, lib.hf_plan_destroy, handle)
+        self.P = host.n_pars
+        self.D = host.n_bins + host.n_aux
+        dev = self.device
+        self.init = torch.as_tensor(host.init, device=dev)
+        self.lo = torch.as_tensor(host.lo, device=dev)
+        self.hi = torch.as_tensor(host.hi, device=dev)
+        self.fixed = torch.as_tensor(host.fixed.astype(np.uint8), device=dev)
+
+    # ------------------------------------------------------------------ evaluation
+    def _prep(self, pars, data):
+        pars = _dev_tensor(pars, self.device)
+        data = _dev_tensor(data, self.device)
+        if pars.dim() == 1:
+            pars = pars.reshape(1, -1)
+        if data.dim() == 1:
+            data = data.reshape(1, -1)
+        B = pars.shape[0]
+        if pars.shape[1] != self.P:
+            raise ValueError(f"pars must have {self.P} columns, got {tuple(pars.shape)}")
+        if data.shape[1] != self.D or data.shape[0] not in (1, B):
+            raise ValueError(f"data must be [{self.D}] or [B, {self.D}], got {tuple(data.shape)}")
+        return pars, data, B
+
+    def logpdf(self, pars, data):
+        """K1: ln L for every row of pars (Model.logpdf, reference pdf.py:957-996)."""
+        pars, data, B = self._prep(pars, data)
+        out = torch.empty(B, dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.hf_logpdf(self._h, _ptr(pars), _ptr(data), data.shape[0], B,
+                                           _ptr(out), _stream()))
+        return out
+
+    def logpdf_grad(self, pars, data):
+        """K2: (ln L [B], d lnL/d theta [B, P])."""
+        pars, data, B = self._prep(pars, data)
+        out = torch.empty(B, dtype=F64, device=self.device)
+        grad = torch.empty(B, self.P, dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.hf_logpdf_grad(self._h, _ptr(pars), _ptr(data), data.shape[0], B,
+                                                _ptr(out), _ptr(grad), _stream()))
+        return out, grad
+
+    def logpdf_grad_host(self, pars_host, data_host, out_host, grad_host):
+        """End-to-end call with HOST buffers (pinned torch CPU tensors): H2D, K2, D2H, sync."""
+        B = pars_host.shape[0]
+        rows = 1 if data_host.dim() == 1 else data_host.shape[0]
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.hf_logpdf_grad_host(
+                self._h, _ptr(pars_host), _ptr(data_host), rows, B, _ptr(out_host),
+                _ptr(grad_host) if grad_host is not None else None, _stream()))
+
+    def expected_data(self, pars):
+        pars = _dev_tensor(pars, self.device)
+        single = pars.dim() == 1
+        if single:
+            pars = pars.reshape(1, -1)
+        out = torch.empty(pars.shape[0], self.D, dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.hf_expected_data(self._h, _ptr(pars), pars.shape[0], _ptr(out), _stream()))
+        return out[0] if single else out
+
+    # ------------------------------------------------------------------ fits
+    def fit(self, data, init=None, lo=None, hi=None, fixed=None, max_iter=None, tol_edm=None,
+            tol_step=None, verbose=0):
+        """K3: N independent bounded fits of 2*NLL.  data [N, D] or [D]; init [N, P] or [P]
+        (fixed parameters keep their init value)."""
+        dev = self.device
+        data = _dev_tensor(data, dev)
+        if data.dim() == 1:
+            data = data.reshape(1, -1)
+        init = self.init if init is None else _dev_tensor(init, dev)
+        if init.dim() == 1:
+            init = init.reshape(1, -1)
+        lo = self.lo if lo is None else _dev_tensor(lo, dev)
+        hi = self.hi if hi is None else _dev_tensor(hi, dev)
+        fixed = self.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
+        N = max(data.shape[0], init.shape[0])
+        if data.shape[1] != self.D or init.shape[1] != self.P:
+            raise ValueError("bad data / init shape")
+        if data.shape[0] not in (1, N) or init.shape[0] not in (1, N):
+            raise ValueError("data and init must have 1 or N rows")
+        opts = _lib.FitOpts()
+        self._lib.hf_fit_default_opts(C.byref(opts))
+        if max_iter is not None:
+            opts.max_iter = int(max_iter)
+        if tol_edm is not None:
+            opts.tol_edm = float(tol_edm)
+        if tol_step is not None:
+            opts.tol_step = float(tol_step)
+        opts.verbose = int(verbose)
+        x = torch.empty(N, self.P, dtype=F64, device=dev)
+        fun = torch.empty(N, dtype=F64, device=dev)
+        status = torch.empty(N, dtype=torch.int32, device=dev)
+        niter = torch.empty(N, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.hf_fit_batch(
+                self._h, _ptr(data), data.shape[0], _ptr(init), init.shape[0], _ptr(lo), _ptr(hi),
+                _ptr(fixed), N, C.byref(opts), _ptr(x), _ptr(fun), _ptr(status), _ptr(niter),
+                _stream()))
+        return FitResult(x, fun, status, niter)
+
+    # ------------------------------------------------------------------ toys
+    def sample_toys(self, pars, n, seed=0, offset=0):
+        """K4: n toys ~ Model.make_pdf(pars).sample((n,)) (reference probability.py:263-274)."""
+        pars = _dev_tensor(pars, self.device).reshape(-1)
+        out = torch.empty(int(n), self.D, dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.hf_sample_toys(self._h, _ptr(pars), int(seed), int(offset), int(n),
+                                                _ptr(out), _stream()))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._lib.hf_plan_launch_count(self._h))
+
+
+# ---------------------------------------------------------------------- per-model cache
+_dev_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def plan_for(model, device=None) -> DevicePlan:
+    """DevicePlan of a live ``pyhf.Model`` (cached with a weak reference to the model)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    try:
+        per_model = _dev_cache.setdefault(model, {})
+    except TypeError:
+        return DevicePlan(cached_plan(model), dev)
+    key = str(dev)
+    if key not in per_model:
+        per_model[key] = DevicePlan(cached_plan(model), dev)
+    return per_model[key]
+
+
+# ---------------------------------------------------------------------- element samplers (backend)
+def sample_poisson(backend, rate, sample_shape):
+    lib = _lib.require()
+    rate = _dev_tensor(rate, backend.device)
+    n = int(np.prod(sample_shape)) if len(sample_shape) else 1
+    m = rate.numel()
+    out = torch.empty((n, m), dtype=F64, device=backend.device)
+    off = backend._toy_offset
+    backend._toy_offset += n
+    _lib.check(lib.hf_sample_poisson(_ptr(rate.reshape(-1)), m, n, backend.seed, off, _ptr(out), _stream()))
+    return out.reshape(tuple(sample_shape) + tuple(rate.shape))
+
+
+def sample_normal(backend, loc, scale, sample_shape):
+    lib = _lib.require()
+    loc, scale = torch.broadcast_tensors(_dev_tensor(loc, backend.device), _dev_tensor(scale, backend.device))
+    loc, scale = loc.contiguous(), scale.contiguous()
+    n = int(np.prod(sample_shape)) if len(sample_shape) else 1
+    m = loc.numel()
+    out = torch.empty((n, m), dtype=F64, device=backend.device)
+    off = backend._toy_offset
+    backend._toy_offset += n
+    _lib.check(lib.hf_sample_normal(_ptr(loc.reshape(-1)), _ptr(scale.reshape(-1)), m, n,
+                                    backend.seed ^ 0x5DEECE66D, off, _ptr(out), _stream()))
+    return out.reshape(tuple(sample_shape) + tuple(loc.shape))
+
+
+# ---------------------------------------------------------------------- test statistics
+_MODES = {"q": 0, "qtilde": 0, "q0": 1, "t": 2, "ttilde": 2}
+
+
+def teststat(fun_fixed, fun_free, muhat, mu, mode="qtilde"):
+    """K5: q = clip(2NLL_fixed - 2NLL_free, 0), zeroed where muhat > mu (q / q~) or muhat < 0 (q0)
+    (reference infer/test_statistics.py:16-60, :507-520)."""
+    lib = _lib.require()
+    n = fun_fixed.numel()
+    q = torch.empty_like(fun_fixed)
+    _lib.check(lib.hf_teststat(_ptr(fun_fixed), _ptr(fun_free), _ptr(muhat.contiguous()), float(mu),
+                               _MODES[mode], n, _ptr(q), _stream()))
+    return q
+
+
+def pvalue_counts(samples, values):
+    """#{samples >= value} per value (EmpiricalDistribution.pvalue, calculators.py:632-640)."""
+    lib = _lib.require()
+    samples = samples.contiguous()
+    values = values.contiguous()
+    counts = torch.empty(values.numel(), dtype=torch.int64, device=samples.device)
+    _lib.check(lib.hf_pvalue_counts(_ptr(samples), samples.numel(), _ptr(values), values.numel(),
+                                    _ptr(counts), _stream()))
+    return counts
+
+
+def qmu_tilde_batch(plan: DevicePlan, mu, data, init=None, lo=None, hi=None, fixed=None,
+                    mode="qtilde", warm_start=False, **fit_kw):
+    """Test statistic of every row of ``data``: one fixed-POI fit and one free fit per row
+    (reference _tmu_like, infer/test_statistics.py:38-60).  Returns a dict of device tensors."""
+    poi = plan.host.poi_index
+    if poi < 0:
+        raise ValueError("the model has no POI")
+    dev = plan.device
+    init = plan.init if init is None else _dev_tensor(init, dev)
+    fixed = plan.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
+    init_fixed = init.clone()
+    init_fixed[..., poi] = float(mu) if mode != "q0" else 0.0
+    fixed_poi = fixed.clone()
+    fixed_poi[poi] = 1
+    rf = plan.fit(data, init_fixed, lo, hi, fixed_poi, **fit_kw)
+    ru = plan.fit(data, rf.x if warm_start else init, lo, hi, fixed, **fit_kw)
+    muhat = ru.x[:, poi].contiguous()
+    q = teststat(rf.fun, ru.fun, muhat, float(mu), mode)
+    return dict(q=q, muhat=muhat, fixed=rf, free=ru)
+
+
+def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=0, init=None,
+                 lo=None, hi=None, fixed=None, mode="qtilde", gather=None, **fit_kw):
+    """Toy-based CLs for one signal strength: the arithmetic of ToyCalculator.distributions /
+    pvalues (reference infer/calculators.py:754-915) with every fit batched on the device.
+
+    ``gather`` (optional) maps a per-rank [n] tensor to the all-rank tensor (see dist.py); toys
+    [toy_offset, toy_offset + ntoys) are this rank's shard."""
+    dev = plan.device
+    data_obs = _dev_tensor(data_obs, dev).reshape(1, -1)
+    init = plan.init if init is None else _dev_tensor(init, dev)
+    fixed = plan.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
+    poi = plan.host.poi_index
+    obs = qmu_tilde_batch(plan, mu_test, data_obs, init, lo, hi, fixed, mode, **fit_kw)
+    # generation points: conditional fits at mu_test and at the background-only value
+    bkg_mu = 1.0 if mode == "q0" else 0.0           # calculators.py:808-817
+    fp = fixed.clone()
+    fp[poi] = 1
+    i_s = init.clone(); i_s[poi] = float(mu_test)
+    i_b = init.clone(); i_b[poi] = bkg_mu
+    gen = plan.fit(data_obs, torch.stack([i_s, i_b]), lo, hi, fp, **fit_kw)
+    sig_toys = plan.sample_toys(gen.x[0], ntoys, seed=seed, offset=toy_offset)
+    bkg_toys = plan.sample_toys(gen.x[1], ntoys, seed=seed + 1, offset=toy_offset)
+    qs = qmu_tilde_batch(plan, mu_test, sig_toys, init, lo, hi, fixed, mode, **fit_kw)
+    qb = qmu_tilde_batch(plan, mu_test, bkg_toys, init, lo, hi, fixed, mode, **fit_kw)
+    q_sig, q_bkg = qs["q"], qb["q"]
+    if gather is not None:
+        q_sig, q_bkg = gather(q_sig), gather(q_bkg)
+    qobs = obs["q"]
+    n_sb = pvalue_counts(q_sig, qobs)[0].item()
+    n_b = pvalue_counts(q_bkg, qobs)[0].item()
+    clsb = n_sb / q_sig.numel()
+    clb = n_b / q_bkg.numel()
+    return dict(qobs=float(qobs[0]), CLsb=clsb, CLb=clb, CLs=(clsb / clb if clb > 0 else float("nan")),
+                q_sig=q_sig, q_bkg=q_bkg, obs=obs, gen=gen,
+                n_failed=int((qs["fixed"].status != 0).sum() + (qs["free"].status != 0).sum()
+                             + (qb["fixed"].status != 0).sum() + (qb["free"].status != 0).sum()))
+
+
+def fp64_peak_tflops():
+    lib = _lib.require()
+    v = C.c_double(0.0)
+    _lib.check(lib.hf_fp64_peak(C.byref(v), _stream()))
+    return v.value

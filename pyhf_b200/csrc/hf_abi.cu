@@ -175,6 +175,9 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     dp.g_sigma = DP(double, o_gsig); dp.p_par = DP(int, o_ppar); dp.p_aux = DP(int, o_paux);
     dp.p_factor = DP(double, o_pfac); dp.par_cons_kind = DP(int, o_ck); dp.par_cons_idx = DP(int, o_ci);
 #undef DP
+    plan->h_bf_par.assign(d->bf_par, d->bf_par + (size_t)K * S * NB);
+    plan->h_hs_par.assign(d->hs_par, d->hs_par + H);
+    plan->h_sf_par.assign(d->sf_par, d->sf_par + NSF);
     cudaGetDevice(&plan->device);
     cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device);
     *out = plan;

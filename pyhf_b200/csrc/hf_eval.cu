@@ -145,8 +145,9 @@ __device__ __forceinline__ void load_factor(const DevPlan& pl, const Work& w, in
 template <int PT, int RC, int TB, bool GRAD>
 __global__ void __launch_bounds__(TB, (PT >= 16) ? 2 : 3)
 hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
-               int64_t data_stride) {
+               int per_point, const int* __restrict__ row_idx) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ int64_t row_off[PT];  // element offset of each point's data row
     constexpr int WPAD = PT + 2;  // 16-byte aligned rows, conflict-free vector stores
     double* c1s = smem;                      // [H][PT]
     double* c2s = c1s + (int64_t)pl.H * PT;  // [H][PT]
@@ -161,6 +162,12 @@ hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restri
         const int h = i / PT, j = i - h * PT;
         c1s[i] = w.c1T[(int64_t)h * ld + pt0 + j];
         c2s[i] = w.c2T[(int64_t)h * ld + pt0 + j];
+    }
+    if (tid < PT) {
+        int64_t pt = pt0 + tid;
+        if (pt >= B) pt = B - 1;
+        const int64_t row = row_idx ? (int64_t)row_idx[pt] : (per_point ? pt : 0);
+        row_off[tid] = row * pl.D;
     }
     __syncthreads();
 
@@ -253,9 +260,7 @@ hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restri
             double term[PT];
 #pragma unroll
             for (int i = 0; i < PT; ++i) {
-                int64_t pt = pt0 + i;
-                if (pt >= B) pt = B - 1;
-                const double n = data[pt * data_stride + bb];
+                const double n = data[row_off[i] + bb];
                 double l = lam[i];
                 bool live = true;
                 if (pl.has_clip_bin && l < pl.clip_bin) {
@@ -373,13 +378,18 @@ hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restri
 // ------------------------------------------------------------------------------------------
 // finish: constraints, scalar-factor gradients, constants, transposition to row-major
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t hf_row_of(const int* row_idx, int per_point, int64_t pt) {
+    return row_idx ? (int64_t)row_idx[pt] : (per_point ? pt : 0);
+}
+
 __global__ void hf_finish_value_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
-                                       const double* __restrict__ data, int64_t data_stride,
-                                       int64_t dconst_stride, double* __restrict__ out) {
+                                       const double* __restrict__ data, int per_point,
+                                       const int* __restrict__ row_idx, double* __restrict__ out) {
     const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= B) return;
-    const double* aux = data + pt * data_stride + pl.NB;
-    double acc = w.mainv[pt] + w.dconst[pt * dconst_stride];
+    const int64_t row = hf_row_of(row_idx, per_point, pt);
+    const double* aux = data + row * pl.D + pl.NB;
+    double acc = w.mainv[pt] + w.dconst[row];
     for (int i = 0; i < pl.NG; ++i) {
         const double th = w.parsT[(int64_t)pl.g_par[i] * ld + pt];
         const double z = (aux[pl.g_aux[i]] - th) / (1.4142135623730951 * pl.g_sigma[i]);
@@ -393,8 +403,8 @@ __global__ void hf_finish_value_kernel(DevPlan pl, Work w, int64_t B, int64_t ld
 }
 
 __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
-                                      const double* __restrict__ data, int64_t data_stride,
-                                      double* __restrict__ grad) {
+                                      const double* __restrict__ data, int per_point,
+                                      const int* __restrict__ row_idx, double* __restrict__ grad) {
     // 32 points x 32 parameters per block; transposed through shared memory so that both the
     // batch-major reads and the row-major writes coalesce
     __shared__ double tile[32][33];
@@ -436,10 +446,12 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
             if (ck == 1) {
                 const int i = pl.par_cons_idx[p];
                 const double sg = pl.g_sigma[i];
-                g += (data[pt * data_stride + pl.NB + pl.g_aux[i]] - th) / (sg * sg);
+                const int64_t row = hf_row_of(row_idx, per_point, pt);
+                g += (data[row * pl.D + pl.NB + pl.g_aux[i]] - th) / (sg * sg);
             } else if (ck == 2) {
                 const int i = pl.par_cons_idx[p];
-                g += data[pt * data_stride + pl.NB + pl.p_aux[i]] / th - pl.p_factor[i];
+                const int64_t row = hf_row_of(row_idx, per_point, pt);
+                g += data[row * pl.D + pl.NB + pl.p_aux[i]] / th - pl.p_factor[i];
             }
         }
         tile[j][tx] = g;
@@ -502,8 +514,8 @@ __global__ void hf_expected_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 template <int PT, int RC, int TB>
-static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data,
-                       int64_t data_stride, bool grad, cudaStream_t st) {
+static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_point,
+                       const int* row_idx, bool grad, cudaStream_t st) {
     const DevPlan& pl = plan->d;
     size_t smem = sizeof(double) * (size_t)(2 * pl.H * PT);
     if (grad) smem += sizeof(double) * (size_t)pl.R * TB * (PT + 2);
@@ -511,11 +523,11 @@ static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data,
     if (grad) {
         auto k = hf_main_kernel<PT, RC, TB, true>;
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, data_stride);
+        k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx);
     } else {
         auto k = hf_main_kernel<PT, RC, TB, false>;
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, data_stride);
+        k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx);
     }
     HF_CUDA_OK(cudaGetLastError());
     plan->launches++;
@@ -539,10 +551,10 @@ static int pick_pt(const hf_plan* plan, bool grad, int64_t B) {
 }
 
 int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
-                   int64_t B, double* out, double* grad, cudaStream_t st) {
+                   int64_t B, double* out, double* grad, cudaStream_t st, const int* row_idx) {
     if (B <= 0) return HF_OK;
     const DevPlan& pl = plan->d;
-    if (data_rows != 1 && data_rows != B) {
+    if (!row_idx && data_rows != 1 && data_rows != B) {
         hf_set_error("data_rows must be 1 or B (got %lld, B=%lld)", (long long)data_rows, (long long)B);
         return HF_ERR_INVALID;
     }
@@ -556,7 +568,7 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
     int rc = hf_ensure_work(plan, ld, data_rows);
     if (rc) return rc;
     Work& w = plan->w;
-    const int64_t dstride = (data_rows == 1) ? 0 : pl.D;
+    const int per_point = (data_rows == 1) ? 0 : 1;
 
     {
         dim3 grid((unsigned)(ld / 32), (unsigned)((pl.P + 31) / 32));
@@ -581,25 +593,25 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
 
     // point tile: RC = rows per register tile
     if (PT == 16) {
-        if (pl.R >= 3 || pl.R == 0) rc = launch_main<16, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
-        else if (pl.R == 2) rc = launch_main<16, 2, 128>(plan, B, ld, data, dstride, do_grad, st);
-        else rc = launch_main<16, 1, 128>(plan, B, ld, data, dstride, do_grad, st);
+        if (pl.R >= 3 || pl.R == 0) rc = launch_main<16, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        else if (pl.R == 2) rc = launch_main<16, 2, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        else rc = launch_main<16, 1, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     } else if (PT == 8) {
-        if (pl.R >= 3 || pl.R == 0) rc = launch_main<8, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
-        else rc = launch_main<8, 2, 128>(plan, B, ld, data, dstride, do_grad, st);
+        if (pl.R >= 3 || pl.R == 0) rc = launch_main<8, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        else rc = launch_main<8, 2, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     } else if (PT == 4) {
-        rc = launch_main<4, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
+        rc = launch_main<4, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     } else {
-        rc = launch_main<2, 4, 128>(plan, B, ld, data, dstride, do_grad, st);
+        rc = launch_main<2, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     }
     if (rc) return rc;
 
-    hf_finish_value_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(
-        pl, w, B, ld, data, dstride, (data_rows == 1) ? 0 : 1, out);
+    hf_finish_value_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pl, w, B, ld, data, per_point,
+                                                                        row_idx, out);
     plan->launches++;
     if (do_grad) {
         dim3 grid((unsigned)((B + 31) / 32), (unsigned)((pl.P + 31) / 32));
-        hf_finish_grad_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, B, ld, data, dstride, grad);
+        hf_finish_grad_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, B, ld, data, per_point, row_idx, grad);
         plan->launches++;
     }
     HF_CUDA_OK(cudaGetLastError());

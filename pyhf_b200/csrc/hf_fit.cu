@@ -1,0 +1,648 @@
+// K3: batched bounded minimiser of 2*NLL -- lock-step projected Newton on the device.
+//
+// Replaces scipy.optimize.minimize(method="SLSQP") as driven by optimize/opt_scipy.py:46-105 under
+// infer/mle.py:69-205.  The algorithm is the one prototyped (and pinned against the reference's
+// fits) in oracle/fit_proto.py:
+//
+//   * every fit advances one trial point per round; all trial points of a round go through ONE
+//     batched K2 launch (hf_eval_launch), so histosys tables are shared by all toys of a CTA tile;
+//   * curvature = forward differences of the ANALYTIC gradient: the perturbed points of every fit
+//     that needs a Hessian form another K2 batch.  Per-bin ("local") parameters that never share
+//     a bin are perturbed together (graph colouring), so a Hessian costs n_global + n_colours
+//     gradient evaluations instead of P;
+//   * far from the minimum the exact Hessian of a HistFactory NLL is often indefinite; there the
+//     Fisher matrix (= Hessian on the Asimov dataset of the current point, always PSD) is used;
+//     once the estimated distance to the minimum is small the exact Hessian takes over;
+//   * one CTA per fit solves the reduced Newton system (active-set projection on the box bounds,
+//     fixed parameters frozen) by an in-shared-memory packed Cholesky factorisation with
+//     diagonal loading when the matrix is not positive definite;
+//   * projected backtracking line search with an Armijo test (one trial per round).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "hf_internal.cuh"
+
+namespace {
+
+constexpr double kFdStep = 1e-5;
+constexpr double kArmijo = 1e-4;
+constexpr int kDirThreads = 128;
+
+struct FitDev {
+    int P, D, ncol, nglob, ncolors;
+    int64_t NC;
+    // per-fit state
+    double *X, *G, *Dd, *XT, *GT, *VT, *F, *T, *EDM, *EDMPREV, *H, *Hshared;
+    int *done, *need_dir, *own, *status, *niter, *refresh, *rlist, *counters;
+    // structure
+    const int* colpar;   // [nglob]  global free parameters, one FD column each
+    const int* pcolor;   // [P]      colour of a free local parameter, -1 global, -2 fixed
+    const int* partner;  // [P][ncolors]
+    const int* pcol;     // [P]      FD column index of a global free parameter, else -1
+    const double *lo, *hi;
+    const uint8_t* fixed;
+    double* chol_scratch;  // global-memory factor storage for n > smem capacity
+    int chol_in_smem;
+    double tol_edm, tol_step, refresh_ratio, exact_below;
+    int max_iter;
+};
+
+__device__ __forceinline__ double fd_step(double x) { return kFdStep * fmax(1.0, fabs(x)); }
+
+// ---------------------------------------------------------------- state initialisation
+__global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64_t init_rows) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.NC * s.P) return;
+    const int64_t i = idx / s.P;
+    const int p = (int)(idx - i * s.P);
+    double v = init[(init_rows == 1 ? 0 : i) * s.P + p];
+    if (!s.fixed[p]) v = fmin(fmax(v, s.lo[p]), s.hi[p]);
+    s.X[idx] = v;
+    s.XT[idx] = v;
+    if (p == 0) {
+        s.done[i] = 0; s.need_dir[i] = 1; s.own[i] = 0; s.status[i] = 1; s.niter[i] = 0;
+        s.refresh[i] = 0; s.T[i] = 1.0; s.EDM[i] = INFINITY; s.EDMPREV[i] = INFINITY;
+    }
+}
+
+// F = -2 * logpdf, G = -2 * grad for the start point
+__global__ void fit_adopt_kernel(FitDev s) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.NC * s.P) return;
+    const int64_t i = idx / s.P;
+    s.G[idx] = -2.0 * s.GT[idx];
+    if (idx - i * s.P == 0) {
+        const double f = -2.0 * s.VT[i];
+        s.F[i] = f;
+        if (!isfinite(f)) { s.done[i] = 1; s.status[i] = 2; }
+    }
+}
+
+// ---------------------------------------------------------------- Hessian by finite differences
+// points of refresh entry r: r*(ncol+1) + c, c < ncol perturbed columns, c == ncol base point
+__global__ void fit_fd_points_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
+                                     double* __restrict__ XP, int* __restrict__ row_idx) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t npts = nlist * (s.ncol + 1);
+    if (idx >= npts * s.P) return;
+    const int64_t pt = idx / s.P;
+    const int p = (int)(idx - pt * s.P);
+    const int64_t r = pt / (s.ncol + 1);
+    const int c = (int)(pt - r * (s.ncol + 1));
+    const int64_t toy = list[r];
+    double v = s.X[toy * s.P + p];
+    if (c < s.nglob) {
+        if (s.colpar[c] == p) v += fd_step(v);
+    } else if (c < s.ncol) {
+        if (s.pcolor[p] == c - s.nglob) v += fd_step(v);
+    }
+    XP[idx] = v;
+    if (p == 0) row_idx[pt] = (int)r;
+}
+
+// data row per refresh entry: Asimov (Fisher mode) or the fit's own data (exact mode)
+__global__ void fit_fd_rows_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
+                                   const int* __restrict__ mode, const double* __restrict__ data,
+                                   int64_t data_rows, int64_t toy0, const double* __restrict__ asimov,
+                                   double* __restrict__ DR) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nlist * s.D) return;
+    const int64_t r = idx / s.D;
+    const int j = (int)(idx - r * s.D);
+    const int64_t toy = list[r];
+    const int m = mode ? mode[toy] : 1;
+    DR[idx] = (m == 1) ? asimov[idx] : data[(data_rows == 1 ? 0 : toy0 + toy) * s.D + j];
+}
+
+__global__ void fit_gather_x_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
+                                    double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nlist * s.P) return;
+    const int64_t r = idx / s.P;
+    out[idx] = s.X[(int64_t)list[r] * s.P + (idx - r * s.P)];
+}
+
+__device__ __forceinline__ double fd_entry(const FitDev& s, const double* __restrict__ gp,
+                                           const double* __restrict__ xrow, int i, int j) {
+    // d(grad 2NLL)_i / d x_j for free i, j (unsymmetrised); gp = gradients of the entry's points
+    const int P = s.P;
+    const double* base = gp + (int64_t)s.ncol * P;
+    const int cj = s.pcol[j];
+    if (cj >= 0) return -2.0 * (gp[(int64_t)cj * P + i] - base[i]) / fd_step(xrow[j]);
+    // j local
+    const int ci = s.pcol[i];
+    if (ci >= 0) return -2.0 * (gp[(int64_t)ci * P + j] - base[j]) / fd_step(xrow[i]);  // symmetry
+    const int col = s.pcolor[j];
+    if (s.partner[(int64_t)i * s.ncolors + col] != j) return 0.0;
+    return -2.0 * (gp[(int64_t)(s.nglob + col) * P + i] - base[i]) / fd_step(xrow[j]);
+}
+
+__global__ void fit_fd_assemble_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
+                                       const double* __restrict__ GP, double* __restrict__ Hdst,
+                                       int to_shared) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t PP = (int64_t)s.P * s.P;
+    if (idx >= nlist * PP) return;
+    const int64_t r = idx / PP;
+    const int64_t e = idx - r * PP;
+    const int i = (int)(e / s.P), j = (int)(e - (int64_t)i * s.P);
+    const int64_t toy = list[r];
+    double v;
+    if (s.fixed[i] || s.fixed[j]) {
+        v = (i == j) ? 1.0 : 0.0;
+    } else {
+        const double* gp = GP + r * (int64_t)(s.ncol + 1) * s.P;
+        const double* xrow = s.X + toy * s.P;
+        v = 0.5 * (fd_entry(s, gp, xrow, i, j) + fd_entry(s, gp, xrow, j, i));
+    }
+    double* dst = to_shared ? Hdst : (Hdst + toy * PP);
+    dst[e] = v;
+}
+
+// ---------------------------------------------------------------- Newton direction (one CTA per fit)
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
+
+// packed lower-triangular Cholesky (Crout by columns), 2 barriers per column
+__device__ bool chol_factor(double* A, int n, int tid, int nth, int* s_flag) {
+    for (int j = 0; j < n; ++j) {
+        for (int i = j + tid; i < n; i += nth) {
+            const double* ri = A + tri(i, 0);
+            const double* rj = A + tri(j, 0);
+            double acc = ri[j];
+            for (int k = 0; k < j; ++k) acc = fma(-ri[k], rj[k], acc);
+            A[tri(i, j)] = acc;
+        }
+        __syncthreads();
+        const double piv = A[tri(j, j)];
+        if (!(piv > 0.0) || !isfinite(piv)) {
+            // uniform decision: every thread reads the same value
+            __syncthreads();
+            return false;
+        }
+        const double l = sqrt(piv);
+        __syncthreads();
+        for (int i = j + tid; i < n; i += nth) A[tri(i, j)] = (i == j) ? l : A[tri(i, j)] / l;
+        __syncthreads();
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kDirThreads)
+fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int allow_refresh) {
+    extern __shared__ __align__(16) double sm[];
+    const int P = s.P;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int64_t toy = list ? (int64_t)list[blockIdx.x] : (int64_t)blockIdx.x;
+    if (toy >= s.NC) return;
+    if (s.done[toy] || !s.need_dir[toy]) return;
+
+    // shared layout: b[P] | map[P] (int) | packed A (if it fits)
+    double* bvec = sm;
+    int* fidx = reinterpret_cast<int*>(bvec + P);
+    double* A = s.chol_in_smem ? (bvec + P + (P + 1) / 2 + 1)
+                               : (s.chol_scratch + (int64_t)blockIdx.x * ((int64_t)P * (P + 1) / 2));
+    __shared__ int s_n;
+    __shared__ double s_red[kDirThreads / 32];
+    __shared__ int s_flag;
+
+    const double* x = s.X + toy * P;
+    const double* g = s.G + toy * P;
+    // active set (serial compaction keeps the free list ordered; P is small)
+    if (tid == 0) {
+        int n = 0;
+        for (int p = 0; p < P; ++p) {
+            const bool act = s.fixed[p] || (x[p] <= s.lo[p] && g[p] > 0.0) ||
+                             (x[p] >= s.hi[p] && g[p] < 0.0);
+            if (!act) fidx[n++] = p;
+        }
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    const double* Hsrc = s.own[toy] ? (s.H + toy * (int64_t)P * P) : s.Hshared;
+
+    double maxdiag = 0.0;
+    for (int i = tid; i < n; i += nth) maxdiag = fmax(maxdiag, fabs(Hsrc[(int64_t)fidx[i] * P + fidx[i]]));
+    for (int o = 16; o > 0; o >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(0xffffffffu, maxdiag, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = maxdiag;
+    __syncthreads();
+    maxdiag = 0.0;
+    for (int k = 0; k < nth / 32; ++k) maxdiag = fmax(maxdiag, s_red[k]);
+    __syncthreads();
+
+    double tau = 0.0;
+    bool ok = false;
+    for (int attempt = 0; attempt < 40 && !ok; ++attempt) {
+        const int ntri = n * (n + 1) / 2;
+        for (int e = tid; e < ntri; e += nth) {
+            // e -> (i, j)
+            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (tri(i, 0) > e) --i;
+            while (tri(i + 1, 0) <= e) ++i;
+            const int j = e - tri(i, 0);
+            double v = Hsrc[(int64_t)fidx[i] * P + fidx[j]];
+            if (i == j) v += tau;
+            A[e] = v;
+        }
+        __syncthreads();
+        ok = chol_factor(A, n, tid, nth, &s_flag);
+        if (!ok) tau = (tau == 0.0) ? 1e-8 * fmax(maxdiag, 1e-300) : tau * 10.0;
+    }
+    if (!ok) {
+        if (tid == 0) { s.done[toy] = 1; s.status[toy] = 2; }
+        return;
+    }
+    // solve L z = -g_F (column oriented), then L^T d = z
+    for (int i = tid; i < n; i += nth) bvec[i] = -g[fidx[i]];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        if (tid == 0) bvec[k] /= A[tri(k, k)];
+        __syncthreads();
+        const double zk = bvec[k];
+        for (int i = k + 1 + tid; i < n; i += nth) bvec[i] = fma(-A[tri(i, k)], zk, bvec[i]);
+        __syncthreads();
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        if (tid == 0) bvec[k] /= A[tri(k, k)];
+        __syncthreads();
+        const double dk = bvec[k];
+        const double* rk = A + tri(k, 0);
+        for (int i = tid; i < k; i += nth) bvec[i] = fma(-rk[i], dk, bvec[i]);
+        __syncthreads();
+    }
+    // edm = -g_F . d_F ; step = max |d|
+    double edm = 0.0, step = 0.0;
+    for (int i = tid; i < n; i += nth) {
+        edm = fma(-g[fidx[i]], bvec[i], edm);
+        step = fmax(step, fabs(bvec[i]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        edm += __shfl_xor_sync(0xffffffffu, edm, o);
+        step = fmax(step, __shfl_xor_sync(0xffffffffu, step, o));
+    }
+    __shared__ double s_red2[kDirThreads / 32];
+    if ((tid & 31) == 0) { s_red[tid >> 5] = edm; s_red2[tid >> 5] = step; }
+    __syncthreads();
+    edm = 0.0; step = 0.0;
+    for (int k = 0; k < nth / 32; ++k) { edm += s_red[k]; step = fmax(step, s_red2[k]); }
+
+    if (allow_refresh) {
+        const bool slow = edm > s.refresh_ratio * s.EDMPREV[toy];
+        const bool want = s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm;
+        if (want) {
+            if (tid == 0) {
+                s.refresh[toy] = (edm < s.exact_below) ? 2 : 1;
+                const int k = atomicAdd(&s.counters[0], 1);
+                s.rlist[k] = (int)toy;
+            }
+            return;  // need_dir stays set: the direction is recomputed after the refresh
+        }
+    }
+    double* d = s.Dd + toy * P;
+    for (int p = tid; p < P; p += nth) d[p] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nth) d[fidx[i]] = bvec[i];
+    if (tid == 0) {
+        s.EDM[toy] = edm;
+        s.EDMPREV[toy] = edm;
+        s.T[toy] = 1.0;
+        s.need_dir[toy] = 0;
+        if (!isfinite(edm)) { s.done[toy] = 1; s.status[toy] = 2; }
+        else if (edm < s.tol_edm && step < s.tol_step) { s.done[toy] = 1; s.status[toy] = 0; }
+    }
+}
+
+__global__ void fit_mark_own_kernel(FitDev s, const int* __restrict__ list, int64_t nlist) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nlist) s.own[list[r]] = 1;
+}
+
+// ---------------------------------------------------------------- trial point / acceptance
+__global__ void fit_trial_kernel(FitDev s) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.NC * s.P) return;
+    const int64_t i = idx / s.P;
+    const int p = (int)(idx - i * s.P);
+    double v = s.X[idx];
+    if (!s.done[i] && !s.fixed[p]) v = fmin(fmax(v + s.T[i] * s.Dd[idx], s.lo[p]), s.hi[p]);
+    s.XT[idx] = v;
+}
+
+// one warp per fit
+__global__ void fit_accept_kernel(FitDev s) {
+    const int64_t toy = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (toy >= s.NC) return;
+    if (s.done[toy]) return;
+    const int P = s.P;
+    const double* x = s.X + toy * P;
+    const double* xt = s.XT + toy * P;
+    const double* g = s.G + toy * P;
+    double dec = 0.0;
+    for (int p = lane; p < P; p += 32) dec = fma(g[p], xt[p] - x[p], dec);
+    for (int o = 16; o > 0; o >>= 1) dec += __shfl_xor_sync(0xffffffffu, dec, o);
+    const double f = s.F[toy];
+    const double ft = -2.0 * s.VT[toy];
+    const double slack = 4e-15 * fmax(1.0, fabs(f));
+    const bool ok = isfinite(ft) && (ft <= f + kArmijo * dec + slack);
+    if (ok) {
+        for (int p = lane; p < P; p += 32) {
+            s.X[toy * P + p] = xt[p];
+            s.G[toy * P + p] = -2.0 * s.GT[toy * P + p];
+        }
+        if (lane == 0) {
+            s.F[toy] = ft;
+            s.need_dir[toy] = 1;
+            const int it = s.niter[toy] + 1;
+            s.niter[toy] = it;
+            if (it >= s.max_iter) { s.done[toy] = 1; s.status[toy] = 1; }
+            else atomicAdd(&s.counters[1], 1);
+        }
+    } else if (lane == 0) {
+        const double t = s.T[toy];
+        if (t < 1e-4) {
+            s.done[toy] = 1;
+            s.status[toy] = (s.EDM[toy] < 1e-7) ? 0 : 2;
+        } else {
+            s.T[toy] = 0.5 * t;
+            atomicAdd(&s.counters[1], 1);
+        }
+    }
+}
+
+__global__ void fit_finish_kernel(FitDev s, int64_t toy0, double* __restrict__ x,
+                                  double* __restrict__ fun, int32_t* __restrict__ status,
+                                  int32_t* __restrict__ niter) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.NC * s.P) return;
+    const int64_t i = idx / s.P;
+    x[(toy0 + i) * s.P + (idx - i * s.P)] = s.X[idx];
+    if (idx - i * s.P == 0) {
+        fun[toy0 + i] = s.F[i];
+        status[toy0 + i] = s.status[i];
+        if (niter) niter[toy0 + i] = s.niter[i];
+    }
+}
+
+// ---------------------------------------------------------------- host side
+struct Carver {
+    char* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) / 256 * 256;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += sizeof(T) * n;
+        return p;
+    }
+};
+
+void build_fd_structure(hf_plan* plan) {
+    if (plan->fd_ready) return;
+    const int P = plan->P, NB = plan->NB, S = plan->S, K = plan->K;
+    // a parameter is "local" when it only ever acts as a per-bin factor, on exactly one bin
+    std::vector<int> bin_of(P, -1);
+    std::vector<char> global(P, 0), seen(P, 0);
+    for (int p : plan->h_hs_par) global[p] = 1;
+    for (int p : plan->h_sf_par) global[p] = 1;
+    for (int k = 0; k < K; ++k)
+        for (int s = 0; s < S; ++s)
+            for (int b = 0; b < NB; ++b) {
+                const int p = plan->h_bf_par[((size_t)k * S + s) * NB + b];
+                if (p < 0) continue;
+                seen[p] = 1;
+                if (bin_of[p] == -1) bin_of[p] = b;
+                else if (bin_of[p] != b) global[p] = 1;
+            }
+    for (int p = 0; p < P; ++p)
+        if (!seen[p]) global[p] = 1;  // parameters without any effect still need a column
+    // colour = rank among the local parameters of the same bin
+    std::vector<std::vector<int>> per_bin(NB);
+    for (int p = 0; p < P; ++p)
+        if (!global[p]) per_bin[bin_of[p]].push_back(p);
+    int ncolors = 0;
+    for (auto& v : per_bin) ncolors = std::max<int>(ncolors, (int)v.size());
+    plan->fd_ncolors = ncolors;
+    plan->fd_color.assign(P, -1);
+    plan->fd_partner.assign((size_t)P * std::max(ncolors, 1), -1);
+    for (auto& v : per_bin)
+        for (size_t a = 0; a < v.size(); ++a) {
+            plan->fd_color[v[a]] = (int)a;
+            for (size_t c = 0; c < v.size(); ++c) plan->fd_partner[(size_t)v[a] * ncolors + c] = v[c];
+        }
+    plan->fd_ready = true;
+}
+
+}  // namespace
+
+int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const double* init,
+                  int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
+                  int64_t N, const hf_fit_opts* opts_in, double* x_out, double* fun_out,
+                  int32_t* status_out, int32_t* niter_out, cudaStream_t st) {
+    if (N <= 0) return HF_OK;
+    if ((data_rows != 1 && data_rows != N) || (init_rows != 1 && init_rows != N)) {
+        hf_set_error("data_rows/init_rows must be 1 or N");
+        return HF_ERR_INVALID;
+    }
+    hf_fit_opts opts;
+    hf_fit_default_opts(&opts);
+    if (opts_in) opts = *opts_in;
+    const int P = plan->P, D = plan->D;
+    build_fd_structure(plan);
+
+    // ---- column structure for this fixed mask (host: P is small)
+    std::vector<uint8_t> h_fixed(P);
+    HF_CUDA_OK(cudaMemcpyAsync(h_fixed.data(), fixed, P, cudaMemcpyDeviceToHost, st));
+    HF_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<int32_t> colpar, pcolor(P), pcol(P, -1);
+    std::vector<char> color_used(std::max(plan->fd_ncolors, 1), 0);
+    for (int p = 0; p < P; ++p) {
+        if (h_fixed[p]) { pcolor[p] = -2; continue; }
+        pcolor[p] = plan->fd_color[p];
+        if (pcolor[p] < 0) { pcol[p] = (int)colpar.size(); colpar.push_back(p); }
+        else color_used[pcolor[p]] = 1;
+    }
+    const int nglob = (int)colpar.size();
+    const int ncolors = plan->fd_ncolors;
+    const int ncol = nglob + ncolors;
+    int nfree = 0;
+    for (int p = 0; p < P; ++p) nfree += h_fixed[p] ? 0 : 1;
+
+    // ---- chunking: per-fit Hessians dominate the memory
+    size_t free_b = 0, total_b = 0;
+    HF_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_fit = sizeof(double) * ((size_t)P * P + 6 * (size_t)P + 8) + 64;
+    const size_t budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
+    int64_t NC = std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)(budget / per_fit)));
+    // FD batch: points per K2 launch
+    const int64_t max_pts = std::max<int64_t>((int64_t)(ncol + 1), std::min<int64_t>((int64_t)1 << 18,
+                                (int64_t)(budget / (sizeof(double) * (2 * (size_t)P + 2) + 8))));
+    const int64_t rl_cap = std::max<int64_t>(1, max_pts / (ncol + 1));  // refresh entries per sub-batch
+
+    const size_t tri_bytes = sizeof(double) * (size_t)P * (P + 1) / 2;
+    const size_t dir_smem_small = sizeof(double) * (P + (P + 1) / 2 + 2);
+    const bool chol_in_smem = dir_smem_small + tri_bytes <= 200 * 1024;
+    const int64_t dir_grid_cap = chol_in_smem ? 0 : std::min<int64_t>(NC, 4096);
+
+    Carver cv{nullptr};
+    auto carve = [&](Carver& c, FitDev& s, double*& XP, double*& GP, double*& VP, double*& DR,
+                     double*& AS, double*& XG, int*& ridx, int*& d_colpar, int*& d_pcolor,
+                     int*& d_partner, int*& d_pcol) {
+        s.X = c.take<double>(NC * P); s.G = c.take<double>(NC * P); s.Dd = c.take<double>(NC * P);
+        s.XT = c.take<double>(NC * P); s.GT = c.take<double>(NC * P); s.VT = c.take<double>(NC);
+        s.F = c.take<double>(NC); s.T = c.take<double>(NC); s.EDM = c.take<double>(NC);
+        s.EDMPREV = c.take<double>(NC);
+        s.H = c.take<double>((size_t)NC * P * P); s.Hshared = c.take<double>((size_t)P * P);
+        s.done = c.take<int>(NC); s.need_dir = c.take<int>(NC); s.own = c.take<int>(NC);
+        s.status = c.take<int>(NC); s.niter = c.take<int>(NC); s.refresh = c.take<int>(NC);
+        s.rlist = c.take<int>(NC + 1); s.counters = c.take<int>(8);
+        XP = c.take<double>((size_t)max_pts * P); GP = c.take<double>((size_t)max_pts * P);
+        VP = c.take<double>(max_pts); DR = c.take<double>((size_t)rl_cap * D);
+        AS = c.take<double>((size_t)rl_cap * D);
+        XG = c.take<double>((size_t)rl_cap * P); ridx = c.take<int>(max_pts);
+        d_colpar = c.take<int>(std::max(nglob, 1)); d_pcolor = c.take<int>(P);
+        d_partner = c.take<int>((size_t)P * std::max(ncolors, 1)); d_pcol = c.take<int>(P);
+        s.chol_scratch = chol_in_smem ? nullptr : c.take<double>((size_t)dir_grid_cap * P * (P + 1) / 2);
+    };
+    FitDev s;
+    memset(&s, 0, sizeof(s));
+    double *XP, *GP, *VP, *DR, *AS, *XG;
+    int *ridx, *d_colpar, *d_pcolor, *d_partner, *d_pcol;
+    carve(cv, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol);
+    const size_t need = cv.off + 4096;
+    if (need > plan->fit_bytes) {
+        if (plan->fit_block) cudaFree(plan->fit_block);
+        plan->fit_block = nullptr;
+        plan->fit_bytes = 0;
+        cudaError_t e = cudaMalloc(&plan->fit_block, need);
+        if (e != cudaSuccess) {
+            hf_set_error("cudaMalloc(%zu) for the fit workspace: %s", need, cudaGetErrorString(e));
+            return HF_ERR_NOMEM;
+        }
+        plan->fit_bytes = need;
+    }
+    Carver cv2{(char*)plan->fit_block};
+    carve(cv2, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol);
+    s.P = P; s.D = D; s.ncol = ncol; s.nglob = nglob; s.ncolors = std::max(ncolors, 1);
+    s.colpar = d_colpar; s.pcolor = d_pcolor; s.partner = d_partner; s.pcol = d_pcol;
+    s.lo = lo; s.hi = hi; s.fixed = fixed;
+    s.chol_in_smem = chol_in_smem ? 1 : 0;
+    s.tol_edm = opts.tol_edm; s.tol_step = opts.tol_step; s.refresh_ratio = 0.05; s.exact_below = 10.0;
+    s.max_iter = opts.max_iter;
+    HF_CUDA_OK(cudaMemcpyAsync(d_colpar, colpar.data(), sizeof(int) * nglob, cudaMemcpyHostToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(d_pcolor, pcolor.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(d_pcol, pcol.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
+    if (ncolors > 0)
+        HF_CUDA_OK(cudaMemcpyAsync(d_partner, plan->fd_partner.data(), sizeof(int) * (size_t)P * ncolors,
+                                   cudaMemcpyHostToDevice, st));
+
+    const size_t dir_smem = dir_smem_small + (chol_in_smem ? tri_bytes : 0);
+    HF_CUDA_OK(cudaFuncSetAttribute(fit_direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)dir_smem));
+
+    auto blocks = [](int64_t n, int t) { return (unsigned)((n + t - 1) / t); };
+
+    auto run_hessians = [&](const int* d_list, int64_t nlist, const int* mode, int64_t toy0,
+                            int to_shared) -> int {
+        for (int64_t r0 = 0; r0 < nlist; r0 += rl_cap) {
+            const int64_t nl = std::min<int64_t>(rl_cap, nlist - r0);
+            const int* lst = d_list + r0;
+            fit_gather_x_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, lst, nl, XG);
+            int rc = hf_expected_launch(plan, XG, nl, AS, st);
+            if (rc) return rc;
+            fit_fd_rows_kernel<<<blocks(nl * D, 256), 256, 0, st>>>(s, lst, nl, mode, data, data_rows,
+                                                                    toy0, AS, DR);
+            const int64_t npts = nl * (ncol + 1);
+            fit_fd_points_kernel<<<blocks(npts * P, 256), 256, 0, st>>>(s, lst, nl, XP, ridx);
+            plan->launches += 3;
+            rc = hf_eval_launch(plan, XP, DR, nl, npts, VP, GP, st, ridx);
+            if (rc) return rc;
+            fit_fd_assemble_kernel<<<blocks(nl * (int64_t)P * P, 256), 256, 0, st>>>(
+                s, lst, nl, GP, to_shared ? s.Hshared : s.H, to_shared);
+            plan->launches++;
+        }
+        HF_CUDA_OK(cudaGetLastError());
+        return HF_OK;
+    };
+
+    std::vector<int> h_list;
+    int h_counters[8];
+    const int max_rounds = opts.max_iter * 4 + 40;
+
+    for (int64_t toy0 = 0; toy0 < N; toy0 += NC) {
+        const int64_t nc = std::min<int64_t>(NC, N - toy0);
+        s.NC = nc;
+        const double* init_c = init + (init_rows == 1 ? 0 : toy0 * P);
+        const double* data_c = data + (data_rows == 1 ? 0 : toy0 * D);
+        fit_init_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s, init_c, init_rows);
+        plan->launches++;
+        int rc = hf_eval_launch(plan, s.X, data_c, data_rows == 1 ? 1 : nc, nc, s.VT, s.GT, st);
+        if (rc) return rc;
+        fit_adopt_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s);
+        plan->launches++;
+        // shared start-up curvature: Fisher matrix at the first fit's start point
+        {
+            const int zero = 0;
+            HF_CUDA_OK(cudaMemcpyAsync(s.rlist, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+            rc = run_hessians(s.rlist, 1, nullptr, toy0, 1);
+            if (rc) return rc;
+        }
+        for (int round = 0; round < max_rounds; ++round) {
+            HF_CUDA_OK(cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st));
+            if (chol_in_smem) {
+                fit_direction_kernel<<<(unsigned)nc, kDirThreads, dir_smem, st>>>(s, nullptr, nc, 1);
+                plan->launches++;
+            } else {
+                // global-memory factor storage: bounded number of resident CTAs -> list launches
+                h_list.resize(nc);
+                for (int64_t i = 0; i < nc; ++i) h_list[i] = (int)i;
+                for (int64_t i0 = 0; i0 < nc; i0 += dir_grid_cap) {
+                    const int64_t nb = std::min<int64_t>(dir_grid_cap, nc - i0);
+                    HF_CUDA_OK(cudaMemcpyAsync(ridx, h_list.data() + i0, sizeof(int) * nb,
+                                               cudaMemcpyHostToDevice, st));
+                    fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, ridx, nb, 1);
+                    plan->launches++;
+                    HF_CUDA_OK(cudaStreamSynchronize(st));
+                }
+            }
+            HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+            HF_CUDA_OK(cudaStreamSynchronize(st));
+            const int nrefresh = h_counters[0];
+            if (nrefresh > 0) {
+                rc = run_hessians(s.rlist, nrefresh, s.refresh, toy0, 0);
+                if (rc) return rc;
+                // mark ownership, recompute the directions of the refreshed fits
+                fit_mark_own_kernel<<<blocks(nrefresh, 256), 256, 0, st>>>(s, s.rlist, nrefresh);
+                if (chol_in_smem) {
+                    fit_direction_kernel<<<(unsigned)nrefresh, kDirThreads, dir_smem, st>>>(s, s.rlist, nrefresh, 0);
+                    plan->launches += 2;
+                } else {
+                    for (int64_t i0 = 0; i0 < nrefresh; i0 += dir_grid_cap) {
+                        const int64_t nb = std::min<int64_t>(dir_grid_cap, nrefresh - i0);
+                        fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, s.rlist + i0, nb, 0);
+                        plan->launches++;
+                        HF_CUDA_OK(cudaStreamSynchronize(st));
+                    }
+                }
+            }
+            fit_trial_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s);
+            plan->launches++;
+            rc = hf_eval_launch(plan, s.XT, data_c, data_rows == 1 ? 1 : nc, nc, s.VT, s.GT, st);
+            if (rc) return rc;
+            HF_CUDA_OK(cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st));
+            fit_accept_kernel<<<blocks(nc * 32, 256), 256, 0, st>>>(s);
+            plan->launches++;
+            HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+            HF_CUDA_OK(cudaStreamSynchronize(st));
+            if (opts.verbose) fprintf(stderr, "[hf_fit] round %d: refresh %d live %d\n", round, nrefresh, h_counters[1]);
+            if (h_counters[1] == 0) break;
+        }
+        fit_finish_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s, toy0, x_out, fun_out, status_out, niter_out);
+        plan->launches++;
+        HF_CUDA_OK(cudaGetLastError());
+    }
+    return HF_OK;
+}

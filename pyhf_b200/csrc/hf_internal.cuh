@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/hf_b200.h"
 
 #define HF_MAX_PT 16
@@ -153,8 +155,17 @@ struct hf_plan {
     int sm_count = 148;
     // host copies of small tables the host logic needs
     int P, NB, S, NAUX, NSEG, H, R, NSF, K, NG, NPO, D;
+    std::vector<int32_t> h_bf_par, h_hs_par, h_sf_par;
+    // fit: finite-difference column structure (built lazily by hf_fit.cu)
+    bool fd_ready = false;
+    int fd_ncolors = 0;
+    std::vector<int32_t> fd_color;    // [P]  colour of a per-bin ("local") parameter, -1 = global
+    std::vector<int32_t> fd_partner;  // [P][ncolors] local parameter of that colour on the same bin
 };
 
 int hf_ensure_work(hf_plan* plan, int64_t B, int64_t data_rows);
+// data row of point pt: row_idx[pt] if row_idx, else pt when data_rows == B, else 0
 int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
-                   int64_t B, double* out, double* grad, cudaStream_t st);
+                   int64_t B, double* out, double* grad, cudaStream_t st,
+                   const int* row_idx = nullptr);
+int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out, cudaStream_t st);

@@ -1,0 +1,151 @@
+"""K1/K2 parity (through the C-ABI) against the reference goldens and the numpy oracle.
+
+Tolerance: logpdf rtol 1e-12 in fp64 (BASELINE.json north_star); gradients 1e-10 relative to the
+largest gradient component (autograd oracle through the unmodified reference graph)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SMALL
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _dev_plan(g, cuda):
+    from pyhf_b200.batched import DevicePlan
+
+    return DevicePlan(g.host_plan(), cuda)
+
+
+@pytest.mark.parametrize("name", SMALL + ["c3"])
+def test_logpdf_matches_reference(name, golden, cuda):
+    g = golden(name)
+    plan = _dev_plan(g, cuda)
+    val = plan.logpdf(g["pars"], g["data"]).cpu().numpy()
+    ref = g["logpdf"]
+    assert np.allclose(val, ref, rtol=RTOL, atol=0), (name, val, ref, np.abs(val - ref) / np.abs(ref))
+    # single point, data given per point
+    B = len(ref)
+    val2 = plan.logpdf(g["pars"], np.tile(g["data"], (B, 1))).cpu().numpy()
+    assert np.allclose(val2, ref, rtol=RTOL, atol=0), (name, val2, ref)
+    one = plan.logpdf(g["pars"][0], g["data"]).cpu().numpy()
+    assert one.shape == (1,) and np.allclose(one, ref[:1], rtol=RTOL)
+
+
+@pytest.mark.parametrize("name", SMALL + ["c3"])
+def test_logpdf_grad_matches_autograd(name, golden, cuda):
+    g = golden(name)
+    plan = _dev_plan(g, cuda)
+    val, grad = plan.logpdf_grad(g["pars"], g["data"])
+    val, grad = val.cpu().numpy(), grad.cpu().numpy()
+    assert np.allclose(val, g["logpdf"], rtol=RTOL, atol=0), (name, val, g["logpdf"])
+    ref = g["grad"]
+    scale = np.max(np.abs(ref), axis=1, keepdims=True) + 1e-300
+    err = np.abs(grad - ref) / scale
+    assert err.max() < 1e-10, (name, err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+@pytest.mark.parametrize("name", SMALL + ["c3"])
+def test_expected_data_matches_reference(name, golden, cuda):
+    g = golden(name)
+    plan = _dev_plan(g, cuda)
+    ed = plan.expected_data(g["pars"]).cpu().numpy()
+    ref = g["expected_data"]
+    assert np.allclose(ed, ref, rtol=1e-12, atol=1e-300), (name, np.abs(ed - ref).max())
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_against_oracle_random_batches(name, golden, cuda):
+    """odd batch sizes (ragged point tiles), per-point data, parameters on their bounds"""
+    from oracle import hf_oracle as O
+
+    g = golden(name)
+    hp = g.host_plan()
+    op = g.oracle_plan()
+    plan = _dev_plan(g, cuda)
+    rng = np.random.default_rng(11)
+    for B in (1, 3, 17, 130):
+        width = np.minimum(0.2 * (hp.hi - hp.lo), 1.2)
+        pars = hp.init[None] + rng.normal(0, 1, (B, hp.n_pars)) * width[None]
+        pars = np.clip(pars, hp.lo, hp.hi)
+        pars[:, hp.fixed.astype(bool)] = hp.init[hp.fixed.astype(bool)]
+        if hp.poi_index >= 0 and B > 1:
+            pars[0, hp.poi_index] = hp.lo[hp.poi_index]  # POI on its bound (mu = 0 in q~ fits)
+        lam = O.expected_data(op, pars)
+        data = np.where(np.arange(lam.shape[1])[None] < hp.n_bins, rng.poisson(np.maximum(lam, 0)), lam)
+        data = data.astype(np.float64)
+        v_ref, g_ref = O.logpdf_grad(op, pars, data)
+        v, gr = plan.logpdf_grad(pars, data)
+        v, gr = v.cpu().numpy(), gr.cpu().numpy()
+        fin = np.isfinite(v_ref)
+        assert np.array_equal(fin, np.isfinite(v)), (name, B)
+        assert np.allclose(v[fin], v_ref[fin], rtol=RTOL, atol=0), (name, B, np.abs(v - v_ref)[fin].max())
+        scale = np.max(np.abs(g_ref[fin]), axis=1, keepdims=True) + 1e-300
+        assert (np.abs(gr[fin] - g_ref[fin]) / scale).max() < 1e-10, (name, B)
+
+
+def test_poisson_edge_cases(golden, cuda):
+    """n = 0 with lambda = 0 contributes 0; n > 0 with lambda = 0 gives -inf
+    (reference tests/test_tensor.py:272-321)"""
+    g = golden("hello")
+    plan = _dev_plan(g, cuda)
+    hp = g.host_plan()
+    pars = hp.init.copy()
+    data = g["data"].copy()
+    v0 = plan.logpdf(pars, data).cpu().numpy()
+    assert np.isfinite(v0).all()
+    data[0] = 0.0
+    assert np.isfinite(plan.logpdf(pars, data).cpu().numpy()).all()
+
+
+@pytest.mark.needs_pyhf
+def test_c4_goldens_and_large_batch_properties(golden, cuda):
+    """C4 (1000 bins / 300 NPs): golden points, then B = 4099 against the oracle on a subsample
+    and size-independent properties (row permutation equivariance, batch == singles)."""
+    from oracle import hf_oracle as O
+
+    g = golden("c4")
+    plan = _dev_plan(g, cuda)
+    val, grad = plan.logpdf_grad(g["pars"], g["data"])
+    val, grad = val.cpu().numpy(), grad.cpu().numpy()
+    assert np.allclose(val, g["logpdf"], rtol=RTOL, atol=0), (val, g["logpdf"])
+    scale = np.max(np.abs(g["grad"]), axis=1, keepdims=True)
+    assert (np.abs(grad - g["grad"]) / scale).max() < 1e-10
+    hp = g.host_plan()
+    op = g.oracle_plan()
+    from pyhf_b200 import synth
+
+    is_alpha = np.zeros(hp.n_pars, bool)
+    is_alpha[hp.hs_par] = True
+    is_alpha[hp.sf_par[hp.sf_kind != 0]] = True
+    is_gamma = np.zeros(hp.n_pars, bool)
+    is_gamma[hp.bf_par[hp.bf_par >= 0]] = True
+    B = 4099
+    pars = synth.param_batch(hp.init, hp.lo, hp.hi, is_alpha, is_gamma, hp.poi_index, B, seed=3)
+    v, gr = plan.logpdf_grad(pars, g["data"])
+    sub = np.arange(0, B, 257)
+    v_ref, g_ref = O.logpdf_grad(op, pars[sub], g["data"])
+    assert np.allclose(v.cpu().numpy()[sub], v_ref, rtol=RTOL, atol=0)
+    sc = np.max(np.abs(g_ref), axis=1, keepdims=True)
+    assert (np.abs(gr.cpu().numpy()[sub] - g_ref) / sc).max() < 1e-10
+    perm = torch.randperm(B, device=v.device)
+    v2, gr2 = plan.logpdf_grad(torch.as_tensor(pars, device=v.device)[perm], g["data"])
+    assert torch.equal(v2, v[perm]) or torch.allclose(v2, v[perm], rtol=1e-13, atol=0)
+    assert torch.allclose(gr2, gr[perm], rtol=1e-11, atol=1e-9)
+    v1 = plan.logpdf(pars[:5], g["data"])
+    assert torch.allclose(v1, v[:5], rtol=1e-13, atol=0)
+
+
+def test_host_buffer_entry_point(golden, cuda):
+    g = golden("mixed_code4p_code4")
+    plan = _dev_plan(g, cuda)
+    pars = torch.as_tensor(g["pars"]).pin_memory()
+    data = torch.as_tensor(g["data"]).reshape(1, -1).pin_memory()
+    out = torch.empty(pars.shape[0], dtype=torch.float64).pin_memory()
+    grad = torch.empty_like(pars).pin_memory()
+    plan.logpdf_grad_host(pars, data, out, grad)
+    assert np.allclose(out.numpy(), g["logpdf"], rtol=RTOL, atol=0)
+    scale = np.max(np.abs(g["grad"]), axis=1, keepdims=True)
+    assert (np.abs(grad.numpy() - g["grad"]) / scale).max() < 1e-10

@@ -1,0 +1,109 @@
+"""Drop-in boundary: unchanged pyhf calls under pyhf.set_backend(b200_backend(), b200_optimizer())."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SMALL
+
+pytestmark = [pytest.mark.gpu, pytest.mark.needs_pyhf]
+
+
+@pytest.fixture
+def b200(cuda):
+    import pyhf
+
+    import pyhf_b200
+
+    pyhf.set_backend(pyhf_b200.b200_backend(seed=7), pyhf_b200.b200_optimizer())
+    yield pyhf
+    pyhf.set_backend("numpy", "scipy")
+
+
+def test_readme_hello_world(b200, golden):
+    pyhf = b200
+    g = golden("hello")
+    model = g.model()
+    data = [51, 48] + model.config.auxdata
+    cls_obs, cls_exp = pyhf.infer.hypotest(1.0, data, model, test_stat="qtilde", return_expected_set=True)
+    assert abs(float(cls_obs) - 0.05251497) < 1e-6  # README.rst:63
+    ref = [0.00260626, 0.01382005, 0.06445319, 0.23525641, 0.57303617]
+    assert np.allclose([float(c) for c in cls_exp], ref, atol=1e-6)
+    assert abs(float(cls_obs) - float(g["cls_obs_qtilde"])) < 1e-6
+
+
+def test_model_logpdf_goes_through_k1(b200, golden):
+    pyhf = b200
+    from pyhf_b200 import batched
+
+    g = golden("mixed_code4p_code4")
+    model = g.model()
+    plan = batched.plan_for(model)
+    before = plan.launch_count
+    val = model.logpdf(g["pars"][1], g["data"])
+    assert plan.launch_count > before, "Model.logpdf did not reach the fused kernel"
+    assert tuple(val.shape) == (1,)
+    assert abs(float(val[0]) - g["logpdf"][1]) < 1e-12 * abs(g["logpdf"][1])
+    with pytest.raises(pyhf.exceptions.InvalidPdfParameters):
+        model.logpdf(g["pars"][1][:-1], g["data"])
+    with pytest.raises(pyhf.exceptions.InvalidPdfData):
+        model.logpdf(g["pars"][1], g["data"][:-1])
+    # generic op route (unfused) agrees
+    ed = model.expected_data(g["pars"][1])
+    assert np.allclose(ed.cpu().numpy(), g["expected_data"][1], rtol=1e-12)
+    pyhf.set_backend("numpy", "scipy")
+    assert not hasattr(pyhf.pdf.Model.logpdf, "__wrapped__"), "hook must uninstall on backend change"
+
+
+@pytest.mark.parametrize("name", [n for n in SMALL if n.startswith("val_")])
+def test_validation_cls(name, b200, golden):
+    """the reference's own CLs goldens (tests/test_validation.py) through the plugin"""
+    pyhf = b200
+    g = golden(name)
+    if name == "val_2bin_2channel_coupledhistosys":
+        pytest.skip("bimodal likelihood: local minimum differs from SLSQP's (DESIGN.md)")
+    model = g.model()
+    obs, exp = pyhf.infer.hypotest(g.meta["mu_test"], g["data"].tolist(), model,
+                                   test_stat=g.meta["test_stat"], return_expected_set=True)
+    tol = max(g.meta["tolerance"], 1e-6)
+    assert abs(float(obs) - float(g["known_obs"])) / float(g["known_obs"]) < 5 * tol
+    assert abs(float(obs) - float(g["cls_obs"])) < 1e-6
+    assert np.allclose([float(e) for e in exp], g["cls_exp"], atol=1e-6)
+
+
+def test_fit_return_conventions(b200, golden):
+    pyhf = b200
+    g = golden("hello")
+    model = g.model()
+    data = g["data"].tolist()
+    x = pyhf.infer.mle.fit(data, model)
+    assert isinstance(x, torch.Tensor) and tuple(x.shape) == (model.config.npars,)
+    x, f = pyhf.infer.mle.fit(data, model, return_fitted_val=True)
+    assert f.dim() == 0
+    assert abs(float(f) - float(g["free_fun_tight"])) < 1e-6
+    x, f, res = pyhf.infer.mle.fixed_poi_fit(1.0, data, model, return_fitted_val=True, return_result_obj=True)
+    assert res.success and float(x[model.config.poi_index]) == 1.0
+    assert np.abs(x.cpu().numpy() - g["fixed_x_tight"]).max() < 1e-5
+    with pytest.raises(pyhf.exceptions.Unsupported):
+        pyhf.infer.mle.fit(data, model, method="L-BFGS-B")
+    with pytest.raises(pyhf.exceptions.Unsupported):
+        pyhf.optimizer.minimize(lambda p, d, m: p.sum(), data, model, model.config.suggested_init(),
+                                model.config.suggested_bounds())
+    with pytest.raises(ValueError):  # infer/mle.py:57-66 runs before the optimizer
+        pyhf.infer.mle.fit(data, model, init_pars=[-5.0, 1.0, 1.0])
+
+
+def test_unchanged_toycalculator(b200, golden):
+    """ToyCalculator loop untouched: the first minimize() of each loop fits the whole toy batch"""
+    pyhf = b200
+    g = golden("hello")
+    model = g.model()
+    data = [51, 48] + model.config.auxdata
+    opt = pyhf.optimizer
+    cls_obs, cls_exp = pyhf.infer.hypotest(1.0, data, model, test_stat="qtilde", calctype="toybased",
+                                           ntoys=300, track_progress=False, return_expected_set=True)
+    assert opt._stats["batched_fits"] == 4 * 300, opt._stats
+    assert opt._stats["cache_hits"] >= 4 * 299
+    assert 0.0 <= float(cls_obs) <= 1.0
+    # asymptotic value 0.0525; 300 toys -> MC error ~0.02
+    assert abs(float(cls_obs) - 0.0525) < 0.08
+    assert len(cls_exp) == 5
