@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- the round-end benchmark contract (one JSON line on stdout).
+
+Metric (BASELINE.json): batched logpdf+grad evaluations per second on the synthetic ATLAS-scale
+workspace C4 (1000 bins / 20 channels / 300 parameters: histosys code4p + normsys code4 +
+staterror), B = 65536 parameter points per GPU per step.  A *step* is one pass of the hot path
+(K2: fused log-likelihood + analytic gradient) over one batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference on host cores
+
+Under torchrun (N > 1) every rank evaluates its own B points (weak scaling, no data-path
+collective); elapsed time is the max over ranks (NCCL all-reduce of the device-timed interval).
+
+Keys beyond the base contract:
+  roofline      dominant kernel (hf_main_kernel) against the *measured* fp64 FMA pipe peak
+                (hf_fp64_peak, run live) -- the path is fp64-pipe bound, not HBM bound; the HBM
+                view (algorithmic bytes / MEASURED_PEAKS.json hbm_gbs) is carried in roofline.hbm
+  cpu_baseline  the unmodified reference (pyhf numpy backend, baseline/_ref) or, if it is not
+                staged on this box, the numpy oracle port, on a bounded sample of the same batch
+  toy_fits      secondary metric: batched q~ toy fits/s on C3 (K3 + K4 + K5)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+
+import numpy as np  # noqa: E402
+
+B_PER_GPU = 65536
+FLOP_PER_EVAL = 3.5e6      # forward + gradient on C4 (algorithmic)
+BYTES_PER_EVAL = 8 * (300 + 1 + 300)   # pars in + value/grad out
+METRIC = "batched logpdf+grad evals/s (C4: 1000 bins, 300 parameters, B=65536 per GPU)"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-toys", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- workload
+def c4_inputs(B, seed=0):
+    """C4 plan tables + the parameter batch and observed data of SURVEY.md section 8(d)."""
+    from pyhf_b200 import synth
+
+    model = None
+    try:
+        import pyhf
+
+        from pyhf_b200.plan import extract_plan
+
+        pyhf.set_backend("numpy", "scipy")
+        model = pyhf.Model(synth.spec_c4(), poi_name="mu", validate=False)
+        hp = extract_plan(model)
+        np.random.seed(0)
+        data = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(hp.init)).sample((1,))[0], dtype=np.float64)
+    except ImportError:
+        raise SystemExit("bench.py needs the staged reference (baseline/_ref) to build the C4 workspace")
+    is_alpha = np.zeros(hp.n_pars, bool)
+    is_alpha[hp.hs_par] = True
+    is_alpha[hp.sf_par[hp.sf_kind != 0]] = True
+    is_gamma = np.zeros(hp.n_pars, bool)
+    is_gamma[hp.bf_par[hp.bf_par >= 0]] = True
+    pars = synth.param_batch(hp.init, hp.lo, hp.hi, is_alpha, is_gamma, hp.poi_index, B, seed=seed)
+    return model, hp, pars, data
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+_ref_fn = None
+
+
+def _ref_init(kind, data, plan_arrays):
+    """per-process set-up: build the reference model (or the oracle plan) once"""
+    global _ref_fn
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    if kind == "reference":
+        import pyhf
+
+        from pyhf_b200 import synth
+
+        pyhf.set_backend("numpy", "scipy")
+        model = pyhf.Model(synth.spec_c4(), poi_name="mu", validate=False)
+        _ref_fn = lambda p: model.logpdf(p, data)  # noqa: E731
+    else:
+        from oracle import hf_oracle as O
+
+        pl = O.Plan(plan_arrays)
+        _ref_fn = lambda p: O.logpdf(pl, p, data)  # noqa: E731
+
+
+def _ref_eval(pts):
+    t0 = time.perf_counter()
+    for p in pts:
+        _ref_fn(p)
+    return len(pts), time.perf_counter() - t0
+
+
+class CpuReference:
+    """the reference's own CPU path for this metric on `cores` processes (one thread each)"""
+
+    def __init__(self, kind, data, cores, plan_arrays=None):
+        import multiprocessing as mp
+
+        self.kind, self.cores = kind, cores
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_ref_init,
+                                                 initargs=(kind, data, plan_arrays))
+        self.pool.map(_ref_eval, [np.zeros((0, 1))] * cores)  # wait for the model builds
+
+    def rate(self, pars, evals_per_core):
+        """(logpdf evals/s over all cores, evals, wall seconds) for one bounded sample"""
+        n = max(1, evals_per_core)
+        chunks = [pars[(i * n) % len(pars):(i * n) % len(pars) + n] for i in range(self.cores)]
+        t0 = time.perf_counter()
+        out = self.pool.map(_ref_eval, chunks)
+        wall = time.perf_counter() - t0
+        total = sum(k for k, _ in out)
+        return total / wall, total, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_kind():
+    try:
+        import pyhf  # noqa: F401
+
+        return "reference"
+    except ImportError:
+        return "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = reference_kind()
+    model, hp, pars, data = c4_inputs(4096)
+    cores = len(os.sched_getaffinity(0))
+    P = hp.n_pars
+    ref = CpuReference(kind, data, cores, hp.arrays() if kind == "port" else None)
+    # calibrate, then size a step so that the whole run stays within ~2 minutes
+    r1, _, _ = ref.rate(pars, 2)
+    per_step = int(120.0 * r1 / cores / (args.steps + args.warmup))
+    per_step = max(1, min(per_step, 64))
+    for _ in range(args.warmup):
+        ref.rate(pars, per_step)
+    total, wall = 0, 0.0
+    for _ in range(args.steps):
+        _, k, w = ref.rate(pars, per_step)
+        total += k
+        wall += w
+    ref.close()
+    logpdf_rate = total / wall
+    value = logpdf_rate / (P + 1)   # the reference's gradient = P+1 forward differences (opt_scipy.py:96-105)
+    sample = (f"{per_step} Model.logpdf evals per core per step on {cores} processes; "
+              f"logpdf+grad = (P+1)={P + 1} evals (SLSQP forward differences); "
+              f"{logpdf_rate:.1f} logpdf evals/s all cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": "C4 synthetic 1000-bin/300-NP workspace, logpdf+grad"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- the CUDA arm
+def run_b200(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pyhf_b200 import batched
+
+    B = args.batch
+    model, hp, pars_np, data_np = c4_inputs(B, seed=rank)
+    plan = batched.DevicePlan(hp)
+    dev = plan.device
+    pars = torch.as_tensor(pars_np, device=dev)
+    data = torch.as_tensor(data_np, device=dev).reshape(1, -1)
+    out = torch.empty(B, dtype=torch.float64, device=dev)
+    grad = torch.empty(B, hp.n_pars, dtype=torch.float64, device=dev)
+    lib, h = plan._lib, plan._h
+    ptr, stream = batched._ptr, batched._stream
+
+    def step():
+        batched._lib.check(lib.hf_logpdf_grad(h, ptr(pars), ptr(data), 1, B, ptr(out), ptr(grad), stream()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = batched.fp64_peak_tflops()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    plan.set_timing(True)
+    launches0 = plan.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = plan.launch_count - launches0
+    main_ms, main_n = plan.main_kernel_ms()
+    plan.set_timing(False)
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0])
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C-ABI with HOST buffers (H2D + kernels + D2H inside the timing)
+    pars_h = torch.as_tensor(pars_np).pin_memory()
+    data_h = torch.as_tensor(data_np).reshape(1, -1).pin_memory()
+    out_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    grad_h = torch.empty(B, hp.n_pars, dtype=torch.float64).pin_memory()
+    plan.logpdf_grad_host(pars_h, data_h, out_h, grad_h)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.logpdf_grad_host(pars_h, data_h, out_h, grad_h)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(te[0])
+    # the device-resident result and the host-buffer result are the same numbers
+    assert torch.allclose(out_h, out.cpu(), rtol=1e-13, atol=0)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    main_avg_ms = main_ms / max(main_n, 1)
+    achieved_tf = FLOP_PER_EVAL * B / (main_avg_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp64", "kernel": "hf_main_kernel", "achieved": achieved_tf, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": None,
+        "peak_source": "measured live: hf_fp64_peak (16 independent DFMA chains/thread, 148x8 CTAs)",
+        "algorithmic_flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": B,
+        "kernel_ms_per_launch": main_avg_ms, "kernel_share_of_step": main_ms / ms,
+        "hbm": {"bound": "hbm", "achieved": BYTES_PER_EVAL * B / (main_avg_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s",
+                "frac": BYTES_PER_EVAL * B / (main_avg_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": hbm_src, "algorithmic_bytes_per_eval": BYTES_PER_EVAL},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 synthetic 1000-bin/20-channel/300-NP workspace (histosys code4p + "
+                               "normsys code4 + staterror), batched logpdf+grad",
+                   "batch_per_gpu": B, "parallelism": f"{world} independent shards (no collective)",
+                   "l2": "inputs larger than L2 (pars 157 MB + grad 157 MB per step)"},
+        "clocks": clk, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(pars_h.numel() * 8 + data_h.numel() * 8),
+                "d2h_bytes_per_step": int(grad_h.numel() * 8 + out_h.numel() * 8),
+                "path": "hf_logpdf_grad_host (C-ABI, pinned host buffers)"},
+        "roofline": roofline,
+    }
+
+    if not args.no_toys:
+        try:
+            line["toy_fits"] = toy_fit_metric(batched)
+        except Exception as exc:  # the headline metric must survive a failure of the extra one
+            line["toy_fits"] = {"error": repr(exc)}
+    if not args.no_cpu_baseline and world == 1:
+        kind = reference_kind()
+        cores = len(os.sched_getaffinity(0))
+        ref = CpuReference(kind, data_np, cores, hp.arrays() if kind == "port" else None)
+        r1, _, _ = ref.rate(pars_np, 2)
+        per_core = max(4, min(256, int(15.0 * r1 / cores)))
+        rate, total, wall = ref.rate(pars_np, per_core)
+        ref.close()
+        P = hp.n_pars
+        line["cpu_baseline"] = {
+            "value": rate / (P + 1), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{total} Model.logpdf evals of the same batch on {cores} processes in {wall:.1f}s "
+                      f"({rate:.1f} logpdf/s); logpdf+grad = {P + 1} evals (forward differences, as "
+                      "scipy SLSQP does under the reference)",
+            "logpdf_evals_per_s": rate,
+        }
+    if dist is not None:
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
+def toy_fit_metric(batched, ntoys=20000):
+    """secondary metric: q~ toy fits/s on C3 (config 3), device-resident toys"""
+    import pyhf
+    import torch
+
+    from pyhf_b200 import synth
+    from pyhf_b200.plan import extract_plan
+
+    model = pyhf.Model(synth.spec_c3(), poi_name="mu", validate=False)
+    hp = extract_plan(model)
+    plan = batched.DevicePlan(hp)
+    toys = plan.sample_toys(hp.init, ntoys, seed=11)
+    batched.qmu_tilde_batch(plan, 1.0, toys[:256])
+    torch.cuda.synchronize()
+    l0 = plan.launch_count
+    t0 = time.perf_counter()
+    out = batched.qmu_tilde_batch(plan, 1.0, toys)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = torch.cat([out["fixed"].status, out["free"].status])
+    return {"metric": "q~ toy fits/s (C3: 100 bins, 120 parameters)", "value": 2 * ntoys / dt,
+            "unit": "fits/s", "ntoys": ntoys, "failed_fits": int((st != 0).sum()),
+            "mean_newton_iterations": float(out["free"].niter.float().mean()),
+            "gpu_launches": plan.launch_count - l0}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

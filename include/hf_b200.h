@@ -95,6 +95,11 @@ int hf_plan_create(const hf_plan_desc* desc, hf_plan** out);
 void hf_plan_destroy(hf_plan* plan);
 /* kernels launched by this plan since creation (for bench.py's gpu_launches claim) */
 int64_t hf_plan_launch_count(const hf_plan* plan);
+/* per-kernel timing of the dominant kernel (hf_main_kernel): when enabled, every launch is
+ * bracketed by CUDA events on the launching stream; hf_plan_main_kernel_ms synchronises those
+ * events, returns the summed milliseconds and the number of launches since the last reset */
+int hf_plan_set_timing(hf_plan* plan, int enable);
+int hf_plan_main_kernel_ms(hf_plan* plan, double* ms_out, int64_t* launches_out);
 
 /*
  * K1 fused forward: out[b] = ln L(pars[b] | data[b or 0])

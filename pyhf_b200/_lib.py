@@ -49,6 +49,8 @@ SIGNATURES = {
     "hf_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(_vp)]),
     "hf_plan_destroy": (None, [_vp]),
     "hf_plan_launch_count": (_i64, [_vp]),
+    "hf_plan_set_timing": (C.c_int, [_vp, C.c_int]),
+    "hf_plan_main_kernel_ms": (C.c_int, [_vp, c_dp, C.POINTER(C.c_int64)]),
     "hf_logpdf": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "hf_logpdf_grad": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hf_expected_data": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -21,11 +21,32 @@ import math
 import numpy as np
 import torch
 
-__all__ = ["TorchCarrierBackend", "B200Backend", "b200_backend"]
+__all__ = ["TorchCarrierBackend", "B200Backend", "b200_backend", "DeviceArray"]
 
 
-class _HostScalarMixin:
-    pass
+class DeviceArray(torch.Tensor):
+    """torch.Tensor that behaves where pyhf treats backend tensors as numpy-like:
+
+    * ``np.asarray(t)`` / numpy ``__setitem__`` with a device tensor on the right-hand side
+      (model construction under a CUDA backend: reference modifiers/shapesys.py:168,
+      staterror.py:189 assign backend index tensors into numpy arrays);
+    * negative-step slices (``result_array[idx][::-1]``, infer/intervals/upper_limits.py:16-18).
+    """
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.detach().as_subclass(torch.Tensor).cpu().numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __getitem__(self, key):
+        if isinstance(key, slice) and key.step is not None and key.step < 0:
+            idx = range(*key.indices(self.shape[0]))
+            index = torch.as_tensor(list(idx), dtype=torch.long, device=self.device)
+            return torch.index_select(self, 0, index)
+        return super().__getitem__(key)
+
+
+def _wrap(t):
+    return t.as_subclass(DeviceArray)
 
 
 class _Poisson:
@@ -60,7 +81,7 @@ class _Normal:
 class TorchCarrierBackend:
     """numpy_backend's vocabulary on torch tensors of one device."""
 
-    array_type = torch.Tensor
+    array_type = DeviceArray
     array_subtype = torch.Tensor
 
     def __init__(self, device="cpu", name="torch_carrier", **kwargs):
@@ -83,21 +104,21 @@ class TorchCarrierBackend:
         except KeyError:
             raise KeyError("Invalid dtype: dtype must be float, int, or bool.") from None
         if isinstance(tensor_in, torch.Tensor):
-            return tensor_in.to(device=self.device, dtype=dt)
+            return _wrap(tensor_in.to(device=self.device, dtype=dt))
         if isinstance(tensor_in, (list, tuple)) and tensor_in and any(
             isinstance(t, torch.Tensor) for t in tensor_in
         ):
             # gotcha G2: lists of 0-d tensors (infer/calculators.py:838-869)
-            return torch.stack(
+            return _wrap(torch.stack(
                 [torch.as_tensor(t, dtype=dt, device=self.device) for t in tensor_in]
-            )
-        return torch.as_tensor(np.asarray(tensor_in), device=self.device).to(dt)
+            ))
+        return _wrap(torch.as_tensor(np.asarray(tensor_in), device=self.device).to(dt))
 
     def ones(self, shape, dtype="float"):
-        return torch.ones(shape, dtype=self.dtypemap[dtype], device=self.device)
+        return _wrap(torch.ones(shape, dtype=self.dtypemap[dtype], device=self.device))
 
     def zeros(self, shape, dtype="float"):
-        return torch.zeros(shape, dtype=self.dtypemap[dtype], device=self.device)
+        return _wrap(torch.zeros(shape, dtype=self.dtypemap[dtype], device=self.device))
 
     def tolist(self, tensor_in):
         try:
@@ -109,7 +130,7 @@ class TorchCarrierBackend:
 
     def to_numpy(self, tensor_in):
         if isinstance(tensor_in, torch.Tensor):
-            return tensor_in.detach().cpu().numpy()
+            return tensor_in.detach().as_subclass(torch.Tensor).cpu().numpy()
         return np.asarray(tensor_in)
 
     # ---------------------------------------------------------------- shape ops
@@ -234,14 +255,14 @@ class TorchCarrierBackend:
 
     # ---------------------------------------------------------------- sampling (carrier: torch RNG)
     def _sample_poisson(self, rate, sample_shape):
-        r = rate.expand(sample_shape + tuple(rate.shape))
-        return torch.poisson(r, generator=self._generator)
+        r = rate.as_subclass(torch.Tensor).expand(sample_shape + tuple(rate.shape))
+        return _wrap(torch.poisson(r, generator=self._generator))
 
     def _sample_normal(self, loc, scale, sample_shape):
         loc, scale = torch.broadcast_tensors(self.astensor(loc), self.astensor(scale))
         shape = sample_shape + tuple(loc.shape)
         z = torch.randn(shape, dtype=torch.float64, device=loc.device, generator=self._generator)
-        return loc + scale * z
+        return _wrap(loc + scale * z)
 
 
 class B200Backend(TorchCarrierBackend):
@@ -270,12 +291,12 @@ class B200Backend(TorchCarrierBackend):
     def _sample_poisson(self, rate, sample_shape):
         from . import batched
 
-        return batched.sample_poisson(self, rate, sample_shape)
+        return _wrap(batched.sample_poisson(self, rate, sample_shape))
 
     def _sample_normal(self, loc, scale, sample_shape):
         from . import batched
 
-        return batched.sample_normal(self, loc, scale, sample_shape)
+        return _wrap(batched.sample_normal(self, loc, scale, sample_shape))
 
 
 def b200_backend(**kwargs):

@@ -202,6 +202,16 @@ class DevicePlan:
     def launch_count(self):
         return int(self._lib.hf_plan_launch_count(self._h))
 
+    def set_timing(self, enable=True):
+        """bracket every launch of the dominant kernel with CUDA events (bench.py roofline)"""
+        _lib.check(self._lib.hf_plan_set_timing(self._h, int(bool(enable))))
+
+    def main_kernel_ms(self):
+        """(summed milliseconds, launches) of hf_main_kernel since the last call"""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self._lib.hf_plan_main_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
 
 # ---------------------------------------------------------------------- per-model cache
 _dev_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()

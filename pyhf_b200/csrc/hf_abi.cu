@@ -191,10 +191,35 @@ void hf_plan_destroy(hf_plan* plan) {
     cudaFree(plan->dconst);
     cudaFree(plan->fit_block);
     cudaFree(plan->stage_block);
+    for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
     delete plan;
 }
 
 int64_t hf_plan_launch_count(const hf_plan* plan) { return plan ? plan->launches : 0; }
+
+int hf_plan_set_timing(hf_plan* plan, int enable) {
+    if (!plan) return HF_ERR_INVALID;
+    for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+    plan->ev.clear();
+    plan->timing = enable != 0;
+    return HF_OK;
+}
+
+int hf_plan_main_kernel_ms(hf_plan* plan, double* ms_out, int64_t* launches_out) {
+    if (!plan || !ms_out || !launches_out) return HF_ERR_INVALID;
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < plan->ev.size(); i += 2) {
+        HF_CUDA_OK(cudaEventSynchronize(plan->ev[i + 1]));
+        float ms = 0.f;
+        HF_CUDA_OK(cudaEventElapsedTime(&ms, plan->ev[i], plan->ev[i + 1]));
+        total += ms;
+    }
+    *ms_out = total;
+    *launches_out = (int64_t)(plan->ev.size() / 2);
+    for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+    plan->ev.clear();
+    return HF_OK;
+}
 
 }  // extern "C"
 

@@ -520,6 +520,12 @@ static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data,
     size_t smem = sizeof(double) * (size_t)(2 * pl.H * PT);
     if (grad) smem += sizeof(double) * (size_t)pl.R * TB * (PT + 2);
     const dim3 grid((unsigned)(ld / PT));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (plan->timing) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+    }
     if (grad) {
         auto k = hf_main_kernel<PT, RC, TB, true>;
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -528,6 +534,11 @@ static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data,
         auto k = hf_main_kernel<PT, RC, TB, false>;
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx);
+    }
+    if (plan->timing) {
+        cudaEventRecord(e1, st);
+        plan->ev.push_back(e0);
+        plan->ev.push_back(e1);
     }
     HF_CUDA_OK(cudaGetLastError());
     plan->launches++;

@@ -151,6 +151,8 @@ struct hf_plan {
     void* stage_block = nullptr;
     size_t stage_bytes = 0;
     int64_t launches = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;  // start/stop pairs of hf_main_kernel launches
     int device = 0;
     int sm_count = 148;
     // host copies of small tables the host logic needs
