@@ -287,7 +287,7 @@ hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restri
                 const double nom = pl.nominal[(int64_t)s * NB + bb];
                 // wr0 = w * (prod of per-bin factors) * base  : G_{s,seg} excludes the scalar
                 // factors so that d/dtheta of a normfactor stays finite at theta == 0
-                double wr0[PT], wr[PT];
+                double wr0[PT], wfs_[PT];
 #pragma unroll
                 for (int i = 0; i < PT; ++i) wr0[i] = 1.0;
                 mul_binfactors<PT>(pl, w, ld, pt0, s, bb, wr0);
@@ -302,20 +302,29 @@ hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restri
                         const double r = fb * base;
                         const bool live = !(pl.has_clip_sample && r < pl.clip_sample);
                         const double wl = live ? wgt[i] : 0.0;
-                        wr[i] = wl * r;
+                        wfs_[i] = wl * F[i] * base;   // w * (scalar factors) * base
                         wr0[i] = wl * wr0[i] * base;
                         if (row >= 0) wfs[((int64_t)row * TB + tid) * WPAD + i] = wl * fb;
                     }
                 }
-                // per-bin factors: d/dgamma = w r / gamma
+                // per-bin factors: d/dgamma_k = w * Fseg * base * prod_{k' != k} gamma_k'
+                // (no division: stays finite for a shapefactor sitting on its bound 0)
                 for (int k = 0; k < pl.K; ++k) {
                     const int p = pl.bf_par[((int64_t)k * S + s) * NB + bb];
                     if (p >= 0 && valid) {
+                        double oth[PT];
 #pragma unroll
-                        for (int i = 0; i < PT; ++i) {
-                            const double g = w.parsT[(int64_t)p * ld + pt0 + i];
-                            atomicAdd(&w.gradT[(int64_t)p * ld + pt0 + i], wr[i] / g);
+                        for (int i = 0; i < PT; ++i) oth[i] = wfs_[i];
+                        for (int k2 = 0; k2 < pl.K; ++k2) {
+                            if (k2 == k) continue;
+                            const int p2 = pl.bf_par[((int64_t)k2 * S + s) * NB + bb];
+                            if (p2 < 0) continue;
+#pragma unroll
+                            for (int i = 0; i < PT; ++i) oth[i] *= w.parsT[(int64_t)p2 * ld + pt0 + i];
                         }
+#pragma unroll
+                        for (int i = 0; i < PT; ++i)
+                            atomicAdd(&w.gradT[(int64_t)p * ld + pt0 + i], oth[i]);
                     }
                 }
                 // G_{s,seg} += w * bf * base  (reduced over the bins of a segment)

@@ -144,6 +144,18 @@ def fit_block(model, data, mu_test, tight_tol=1e-12):
     return out
 
 
+def cls_block(model, data, mu, test_stat):
+    """asymptotic CLs (observed + expected band) with the default and the tight reference optimizer"""
+    out = {}
+    for tag, kw in (("", {}), ("_tight", {"tolerance": 1e-12})):
+        pyhf.set_backend("numpy", pyhf.optimize.scipy_optimizer(**kw))
+        obs, exps = pyhf.infer.hypotest(mu, data, model, test_stat=test_stat, return_expected_set=True)
+        out[f"cls_obs{tag}"] = float(obs)
+        out[f"cls_exp{tag}"] = np.array([float(e) for e in exps])
+    pyhf.set_backend("numpy", "scipy")
+    return out
+
+
 def save(name, spec, model, blocks, extra=None):
     plan = extract_plan(model)
     d = {f"plan__{k}": v for k, v in plan.arrays().items()}
@@ -241,9 +253,9 @@ def stage_small():
     data = [51.0, 48.0] + model.config.auxdata
     blocks = eval_block(model, par_batch(model, 6, 1), data)
     blocks.update(fit_block(model, data, 1.0))
-    obs, exp = pyhf.infer.hypotest(1.0, data, model, test_stat="qtilde", return_expected_set=True)
-    blocks["cls_obs_qtilde"] = float(obs)
-    blocks["cls_exp_qtilde"] = np.array([float(e) for e in exp])
+    cb = cls_block(model, data, 1.0, "qtilde")
+    blocks.update({k + "_qtilde" if not k.endswith("_tight") else k.replace("_tight", "_qtilde_tight"): v
+                   for k, v in cb.items()})
     blocks["qmu_tilde"] = float(pyhf.infer.test_statistics.qmu_tilde(
         1.0, data, model, model.config.suggested_init(), model.config.suggested_bounds(),
         model.config.suggested_fixed()))
@@ -261,9 +273,8 @@ def stage_small():
         data = source_data(src, model)
         blocks = eval_block(model, par_batch(model, 6, 2), data)
         blocks.update(fit_block(model, data, mu))
-        obs, exps = pyhf.infer.hypotest(mu, data, model, test_stat=ts, return_expected_set=True)
-        blocks["cls_obs"] = float(obs)
-        blocks["cls_exp"] = np.array([float(e) for e in exps])
+        blocks.update(cls_block(model, data, mu, ts))
+        obs = blocks["cls_obs"]
         blocks["known_obs"] = float(exp["obs"])
         blocks["known_exp"] = np.array(exp["exp"], float)
         assert abs(blocks["cls_obs"] - exp["obs"]) / exp["obs"] < max(tol, 2e-6), (key, obs, exp)

@@ -130,7 +130,8 @@ def test_c3_toy_fits(golden, cuda):
     assert np.abs(out["q"].cpu().numpy() - q_ref).max() < 1e-6
     hp, op = g.host_plan(), g.oracle_plan()
     for i in range(3):
-        _check_optimal(op, hp, out["free"].x[i].cpu().numpy(), g["toys"][i], hp.fixed, tol=5e-5)
+        # curvatures reach 1e4 on C3: |g| ~ sqrt(edm * H) ~ 3e-4 at the 1e-11 edm stopping rule
+        _check_optimal(op, hp, out["free"].x[i].cpu().numpy(), g["toys"][i], hp.fixed, tol=5e-4)
 
 
 def test_batch_equals_singles_and_ragged(golden, cuda):

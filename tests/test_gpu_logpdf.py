@@ -73,9 +73,9 @@ def test_against_oracle_random_batches(name, golden, cuda):
     plan = _dev_plan(g, cuda)
     rng = np.random.default_rng(11)
     for B in (1, 3, 17, 130):
-        width = np.minimum(0.2 * (hp.hi - hp.lo), 1.2)
+        width = np.minimum(0.05 * (hp.hi - hp.lo), 0.6)
         pars = hp.init[None] + rng.normal(0, 1, (B, hp.n_pars)) * width[None]
-        pars = np.clip(pars, hp.lo, hp.hi)
+        pars = np.clip(pars, hp.lo + 0.05, hp.hi)
         pars[:, hp.fixed.astype(bool)] = hp.init[hp.fixed.astype(bool)]
         if hp.poi_index >= 0 and B > 1:
             pars[0, hp.poi_index] = hp.lo[hp.poi_index]  # POI on its bound (mu = 0 in q~ fits)
@@ -141,14 +141,18 @@ def test_c4_goldens_and_large_batch_properties(golden, cuda):
     v, gr = plan.logpdf_grad(pars, g["data"])
     sub = np.arange(0, B, 257)
     v_ref, g_ref = O.logpdf_grad(op, pars[sub], g["data"])
-    assert np.allclose(v.cpu().numpy()[sub], v_ref, rtol=RTOL, atol=0)
-    sc = np.max(np.abs(g_ref), axis=1, keepdims=True)
-    assert (np.abs(gr.cpu().numpy()[sub] - g_ref) / sc).max() < 1e-10
+    fin = np.isfinite(v_ref)
+    assert np.array_equal(fin, np.isfinite(v.cpu().numpy()[sub]))
+    assert np.allclose(v.cpu().numpy()[sub][fin], v_ref[fin], rtol=RTOL, atol=0)
+    sc = np.max(np.abs(g_ref[fin]), axis=1, keepdims=True)
+    assert (np.abs(gr.cpu().numpy()[sub][fin] - g_ref[fin]) / sc).max() < 1e-10
     perm = torch.randperm(B, device=v.device)
     v2, gr2 = plan.logpdf_grad(torch.as_tensor(pars, device=v.device)[perm], g["data"])
-    rel = ((v2 - v[perm]).abs() / v[perm].abs()).max().item()
+    ok = torch.isfinite(v[perm])          # far-out random points may have lambda < 0 -> nan
+    assert torch.equal(ok, torch.isfinite(v2)) and ok.float().mean() > 0.9
+    rel = ((v2 - v[perm]).abs() / v[perm].abs())[ok].max().item()
     assert rel < 1e-12, rel
-    relg = ((gr2 - gr[perm]).abs().max(dim=1).values / gr[perm].abs().max(dim=1).values).max().item()
+    relg = ((gr2 - gr[perm]).abs().max(dim=1).values / gr[perm].abs().max(dim=1).values)[ok].max().item()
     assert relg < 1e-10, relg
     v1 = plan.logpdf(pars[:5], g["data"])
     assert ((v1 - v[:5]).abs() / v[:5].abs()).max().item() < 1e-12

@@ -25,10 +25,15 @@ def test_readme_hello_world(b200, golden):
     model = g.model()
     data = [51, 48] + model.config.auxdata
     cls_obs, cls_exp = pyhf.infer.hypotest(1.0, data, model, test_stat="qtilde", return_expected_set=True)
-    assert abs(float(cls_obs) - 0.05251497) < 1e-6  # README.rst:63
+    exp = [float(c) for c in cls_exp]
+    # (ii) 1e-6 against the reference stack at tolerance=1e-12 ...
+    assert abs(float(cls_obs) - float(g["cls_obs_qtilde_tight"])) < 1e-6
+    assert np.allclose(exp, g["cls_exp_qtilde_tight"], atol=1e-6, rtol=0)
+    # ... and the published README numbers (default SLSQP tolerance: under-converged at ~3e-5 rel,
+    # tight vs default reference differ by exactly that, see tests/golden/make_golden.py)
+    assert abs(float(cls_obs) - 0.05251497) < 2e-6  # README.rst:63
     ref = [0.00260626, 0.01382005, 0.06445319, 0.23525641, 0.57303617]
-    assert np.allclose([float(c) for c in cls_exp], ref, atol=1e-6)
-    assert abs(float(cls_obs) - float(g["cls_obs_qtilde"])) < 1e-6
+    assert np.allclose(exp, ref, rtol=1e-4, atol=0)
 
 
 def test_model_logpdf_goes_through_k1(b200, golden):
@@ -64,10 +69,12 @@ def test_validation_cls(name, b200, golden):
     model = g.model()
     obs, exp = pyhf.infer.hypotest(g.meta["mu_test"], g["data"].tolist(), model,
                                    test_stat=g.meta["test_stat"], return_expected_set=True)
-    tol = max(g.meta["tolerance"], 1e-6)
-    assert abs(float(obs) - float(g["known_obs"])) / float(g["known_obs"]) < 5 * tol
-    assert abs(float(obs) - float(g["cls_obs"])) < 1e-6
-    assert np.allclose([float(e) for e in exp], g["cls_exp"], atol=1e-6)
+    # 1e-6 against the tight reference; the stored known answers come from the default-tolerance
+    # SLSQP, which the reference's own test only pins to 1e-6 .. 3e-4 relative
+    assert abs(float(obs) - float(g["cls_obs_tight"])) < 1e-6
+    assert np.allclose([float(e) for e in exp], g["cls_exp_tight"], atol=1e-6, rtol=0)
+    tol = max(g.meta["tolerance"], 1e-4)
+    assert abs(float(obs) - float(g["known_obs"])) / float(g["known_obs"]) < tol
 
 
 def test_fit_return_conventions(b200, golden):
