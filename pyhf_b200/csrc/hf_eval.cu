@@ -18,6 +18,7 @@
 // constraints.py:100-141,219-262, tensor/numpy_backend.py:435-436,482-490, probability.py:276-299.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "hf_internal.cuh"
 
@@ -143,7 +144,7 @@ __device__ __forceinline__ void load_factor(const DevPlan& pl, const Work& w, in
 }
 
 template <int PT, int RC, int TB, bool GRAD>
-__global__ void __launch_bounds__(TB, (PT >= 16) ? 2 : 3)
+__global__ void __launch_bounds__(TB, (PT >= 16) ? 2 : 4)
 hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
                int per_point, const int* __restrict__ row_idx) {
     extern __shared__ __align__(16) double smem[];
@@ -557,6 +558,10 @@ static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data,
 // smem budget decides the point tile: PT=16 needs (2H*16 + R*128*18)*8 bytes for the gradient.
 static int pick_pt(const hf_plan* plan, bool grad, int64_t B) {
     const DevPlan& pl = plan->d;
+    if (const char* e = getenv("HF_PT")) {  // tuning knob (tools/, not the product default)
+        const int v = atoi(e);
+        if (v == 2 || v == 4 || v == 8 || v == 16) return v;
+    }
     const size_t lim = 200 * 1024;
     auto need = [&](int pt) {
         size_t s = sizeof(double) * (size_t)(2 * pl.H * pt);
