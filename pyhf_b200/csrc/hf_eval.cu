@@ -143,8 +143,8 @@ __device__ __forceinline__ void load_factor(const DevPlan& pl, const Work& w, in
     mul_binfactors<PT>(pl, w, ld, pt0, s, bb, F);
 }
 
-template <int PT, int RC, int TB, bool GRAD>
-__global__ void __launch_bounds__(TB, (PT >= 16) ? 2 : 4)
+template <int PT, int RC, int TB, bool GRAD, int MINB>
+__global__ void __launch_bounds__(TB, MINB)
 hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
                int per_point, const int* __restrict__ row_idx) {
     extern __shared__ __align__(16) double smem[];
@@ -523,7 +523,7 @@ __global__ void hf_expected_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
 // ------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-template <int PT, int RC, int TB>
+template <int PT, int RC, int TB, int MINB>
 static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_point,
                        const int* row_idx, bool grad, cudaStream_t st) {
     const DevPlan& pl = plan->d;
@@ -537,11 +537,11 @@ static int launch_main(hf_plan* plan, int64_t B, int64_t ld, const double* data,
         cudaEventRecord(e0, st);
     }
     if (grad) {
-        auto k = hf_main_kernel<PT, RC, TB, true>;
+        auto k = hf_main_kernel<PT, RC, TB, true, MINB>;
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx);
     } else {
-        auto k = hf_main_kernel<PT, RC, TB, false>;
+        auto k = hf_main_kernel<PT, RC, TB, false, MINB>;
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, TB, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx);
     }
@@ -617,17 +617,21 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
     w.dconst = plan->dconst;
 
     // point tile: RC = rows per register tile
+    int minb = 3;
+    if (const char* e = getenv("HF_MINB")) minb = atoi(e);
     if (PT == 16) {
-        if (pl.R >= 3 || pl.R == 0) rc = launch_main<16, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
-        else if (pl.R == 2) rc = launch_main<16, 2, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
-        else rc = launch_main<16, 1, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        if (pl.R >= 3 || pl.R == 0) rc = launch_main<16, 4, 128, 2>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        else if (pl.R == 2) rc = launch_main<16, 2, 128, 2>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        else rc = launch_main<16, 1, 128, 2>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     } else if (PT == 8) {
-        if (pl.R >= 3 || pl.R == 0) rc = launch_main<8, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
-        else rc = launch_main<8, 2, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        if (pl.R >= 3 || pl.R == 0) {
+            if (minb >= 4) rc = launch_main<8, 4, 128, 4>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+            else rc = launch_main<8, 4, 128, 3>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        } else rc = launch_main<8, 2, 128, 3>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     } else if (PT == 4) {
-        rc = launch_main<4, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        rc = launch_main<4, 4, 128, 4>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     } else {
-        rc = launch_main<2, 4, 128>(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        rc = launch_main<2, 4, 128, 4>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     }
     if (rc) return rc;
 
