@@ -122,7 +122,33 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     for (int i = 0; i < d->n_gauss; ++i) { cons_kind[d->g_par[i]] = 1; cons_idx[d->g_par[i]] = i; }
     for (int i = 0; i < d->n_pois; ++i) { cons_kind[d->p_par[i]] = 2; cons_idx[d->p_par[i]] = i; }
 
+    // DMMA path tables: [tile][chunk][k_local][cell], cell = bin_local * 4 + row, zero padded
+    int n_other = 0, other[2] = {-1, -1};
+    for (int s = 0; s < S; ++s)
+        if (sample_row[s] < 0) {
+            if (n_other < 2) other[n_other] = s;
+            ++n_other;
+        }
+    const bool mma_ok = H > 0 && R <= 4 && S <= 8;
+    const int mma_ntiles = (NB + HF_MMA_BT - 1) / HF_MMA_BT;
+    const int mma_nchunks = (2 * H + HF_MMA_KC - 1) / HF_MMA_KC;
+    std::vector<double> tt;
+    if (mma_ok) {
+        tt.assign((size_t)mma_ntiles * mma_nchunks * HF_MMA_KC * HF_MMA_CS, 0.0);
+        for (int h = 0; h < H; ++h)
+            for (int r = 0; r < R; ++r)
+                for (int b = 0; b < NB; ++b) {
+                    const int tile = b / HF_MMA_BT, bl = b % HF_MMA_BT, cell = bl * 4 + r;
+                    for (int which = 0; which < 2; ++which) {
+                        const int k = 2 * h + which, chunk = k / HF_MMA_KC, kl = k % HF_MMA_KC;
+                        const double v = (which ? d->hs_t2 : d->hs_t1)[((size_t)h * R + r) * NB + b];
+                        tt[(((size_t)tile * mma_nchunks + chunk) * HF_MMA_KC + kl) * HF_MMA_CS + cell] = v;
+                    }
+                }
+    }
+
     Packer pk;
+    const size_t o_tt = pk.add(tt.data(), sizeof(double) * tt.size());
     const size_t o_nom = pk.add(d->nominal, sizeof(double) * S * NB);
     const size_t o_seg = pk.add(d->bin_seg, sizeof(int32_t) * NB);
     const size_t o_hpar = pk.add(d->hs_par, sizeof(int32_t) * H);
@@ -174,6 +200,9 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     dp.bf_par = DP(int, o_bf); dp.g_par = DP(int, o_gpar); dp.g_aux = DP(int, o_gaux);
     dp.g_sigma = DP(double, o_gsig); dp.p_par = DP(int, o_ppar); dp.p_aux = DP(int, o_paux);
     dp.p_factor = DP(double, o_pfac); dp.par_cons_kind = DP(int, o_ck); dp.par_cons_idx = DP(int, o_ci);
+    dp.mma_ok = mma_ok ? 1 : 0; dp.mma_ntiles = mma_ntiles; dp.mma_nchunks = mma_nchunks;
+    dp.mma_nother = n_other; dp.mma_other[0] = other[0]; dp.mma_other[1] = other[1];
+    dp.mma_tt = DP(double, o_tt);
 #undef DP
     plan->h_bf_par.assign(d->bf_par, d->bf_par + (size_t)K * S * NB);
     plan->h_hs_par.assign(d->hs_par, d->hs_par + H);
@@ -231,8 +260,8 @@ int hf_ensure_work(hf_plan* plan, int64_t ld, int64_t data_rows) {
         plan->work_block = nullptr;
         plan->work_ld = 0;
         const int64_t nq = (int64_t)pl.S * pl.NSEG;
-        // [parsT P][c1,c2,dc1,dc2 4H][Fseg,Gseg 2nq][gradT P][mainv 1]
-        const int64_t rows = 2LL * pl.P + 4LL * pl.H + 2 * nq + 1;
+        // [parsT P][c1,c2,dc1,dc2 4H][Fseg,Gseg 2nq][gradT P][mainv 1][coefK KS]
+        const int64_t rows = 2LL * pl.P + 4LL * pl.H + 2 * nq + 1 + (pl.mma_ok ? hf_mma_ks(pl.H) : 0) + 8;
         const size_t bytes = sizeof(double) * (size_t)rows * (size_t)ld + 256;
         cudaError_t e = cudaMalloc(&plan->work_block, bytes);
         if (e != cudaSuccess) {
@@ -254,7 +283,9 @@ int hf_ensure_work(hf_plan* plan, int64_t ld, int64_t data_rows) {
         w.FsegT = p; p += nq * ld;
         w.GsegT = p; p += nq * ld;
         w.gradT = p; p += (int64_t)pl.P * ld;
-        w.mainv = p;
+        w.mainv = p; p += ld;
+        p = (double*)(((uintptr_t)p + 255) / 256 * 256);
+        w.coefK = p;
     }
     if (data_rows > plan->dconst_cap) {
         if (plan->dconst) cudaFree(plan->dconst);

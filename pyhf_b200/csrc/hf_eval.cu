@@ -65,14 +65,13 @@ __global__ void hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
             }
         } else {
             const int q = item - pl.H;
-            double prod = 1.0;
+            double prod = 1.0, logsum = 0.0;
             const int e1 = pl.sf_ptr[q + 1];
             for (int e = pl.sf_ptr[q]; e < e1; ++e) {
                 const double t = w.parsT[(int64_t)pl.sf_par[e] * ld + pt];
-                double f, dl;
-                hf_sf_eval(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, t, f, dl);
-                prod *= f;
+                hf_sf_accum(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, t, prod, logsum);
             }
+            if (logsum != 0.0) prod *= exp(logsum);
             w.FsegT[(int64_t)q * ld + pt] = prod;
         }
     }
@@ -437,18 +436,17 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                 const int q = pl.sfp_q[k];
                 double coef;
                 if (pl.sf_kind[e] == HF_SF_THETA) {
+                    double logsum = 0.0;
                     coef = 1.0;
                     for (int e2 = pl.sf_ptr[q]; e2 < pl.sf_ptr[q + 1]; ++e2) {
                         if (e2 == e) continue;
-                        double f2, dl2;
-                        hf_sf_eval(pl.sf_kind[e2], pl.sf_coef + 8 * (int64_t)e2,
-                                   w.parsT[(int64_t)pl.sf_par[e2] * ld + pt], f2, dl2);
-                        coef *= f2;
+                        hf_sf_accum(pl.sf_kind[e2], pl.sf_coef + 8 * (int64_t)e2,
+                                    w.parsT[(int64_t)pl.sf_par[e2] * ld + pt], coef, logsum);
                     }
+                    if (logsum != 0.0) coef *= exp(logsum);
                 } else {
-                    double f, dl;
-                    hf_sf_eval(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, th, f, dl);
-                    coef = dl * w.FsegT[(int64_t)q * ld + pt];
+                    coef = hf_sf_dlog(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, th) *
+                           w.FsegT[(int64_t)q * ld + pt];
                 }
                 g = fma(coef, w.GsegT[(int64_t)q * ld + pt], g);
             }
@@ -616,6 +614,17 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
     plan->launches++;
     w.dconst = plan->dconst;
 
+    // tensor-core (DMMA) formulation for large batches of plans that qualify
+    bool use_mma = pl.mma_ok && B >= 256;
+    if (const char* e = getenv("HF_MMA")) use_mma = pl.mma_ok && atoi(e) != 0;
+    if (use_mma) {
+        rc = hf_main_mma_launch(plan, B, ld, data, per_point, row_idx, do_grad, st);
+        if (rc != HF_ERR_UNSUPPORTED) {
+            if (rc) return rc;
+            goto finish;
+        }
+    }
+    {
     // point tile: RC = rows per register tile
     int minb = 3;
     if (const char* e = getenv("HF_MINB")) minb = atoi(e);
@@ -634,7 +643,8 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
         rc = launch_main<2, 4, 128, 4>(plan, B, ld, data, per_point, row_idx, do_grad, st);
     }
     if (rc) return rc;
-
+    }
+finish:
     hf_finish_value_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pl, w, B, ld, data, per_point,
                                                                         row_idx, out);
     plan->launches++;

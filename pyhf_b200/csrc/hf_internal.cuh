@@ -39,7 +39,20 @@ struct DevPlan {
     const double* p_factor;      // [NPO]
     const int* par_cons_kind;    // [P] 0 none, 1 gauss, 2 poisson
     const int* par_cons_idx;     // [P] index into g_* / p_*
+    // ---- DMMA path (hf_eval_mma.cu): tables re-tiled for bulk copies into shared memory
+    int mma_ok;                  // plan fits the tensor-core kernel (0 < H, R <= 4, <= 2 other samples)
+    int mma_ntiles;              // bin tiles of HF_MMA_BT bins
+    int mma_nchunks;             // K chunks of HF_MMA_KC columns (column 2h = T1_h, 2h+1 = T2_h)
+    int mma_nother;              // samples without histosys
+    int mma_other[2];            // their sample indices
+    const double* mma_tt;        // [ntiles][nchunks][HF_MMA_KC][HF_MMA_CS] (cell = bin_local*4 + row)
 };
+
+#define HF_MMA_BT 32    // bins per tile
+#define HF_MMA_NC 128   // cells per tile (4 rows per bin)
+#define HF_MMA_CS 132   // padded cell stride: == 4 mod 16 doubles -> conflict-free fragment loads
+#define HF_MMA_KC 40    // K columns per chunk (20 modifiers)
+#define HF_MMA_M 32     // parameter points per CTA
 
 // Per-call scratch, batch-major ("parameter-batch-major": point index fastest) so that warps
 // whose lanes are points read/write coalesced.  ld = padded number of points.
@@ -53,6 +66,7 @@ struct Work {
     double* GsegT;  // [S*NSEG][ld]  sum_{b in seg} w_b r_{s,b}
     double* gradT;  // [P][ld]
     double* mainv;  // [ld]          main-term partial sums
+    double* coefK;  // [ld][KS]      DMMA path: point-major histosys coefficients (c1_h, c2_h interleaved)
     double* dconst; // [data_rows]   -sum lgamma(n+1) - sum ln(sigma sqrt(2pi)) ... (theta-independent)
 };
 
@@ -116,6 +130,48 @@ __host__ __device__ inline void hf_sf_eval(int kind, const double* __restrict__ 
     }
 }
 
+// Branch-free accumulation of one scalar factor into (prod, logsum): F = prod * exp(logsum).
+// Lanes are parameter points, so per-entry branches on alpha would diverge in every warp and
+// each entry would pay for both the polynomial and the exp(); here the outside-range factors
+// exp(+-alpha ln hi/lo) are summed in the log domain and ONE exp() per (sample, channel) is taken.
+__device__ __forceinline__ void hf_sf_accum(int kind, const double* __restrict__ cf, double t,
+                                            double& prod, double& logsum) {
+    if (kind == HF_SF_THETA) {  // kind is uniform across the warp (same entry, different points)
+        prod *= t;
+        return;
+    }
+    const double lnu = cf[0], lnd = cf[1];
+    if (kind == HF_SF_CODE4) {
+        double poly = cf[7];
+#pragma unroll
+        for (int i = 6; i >= 2; --i) poly = fma(poly, t, cf[i]);
+        poly = fma(poly, t, 1.0);
+        const bool inside = (t > -1.0) && (t < 1.0);
+        prod *= inside ? poly : 1.0;
+        logsum += inside ? 0.0 : ((t >= 1.0) ? t * lnu : -t * lnd);
+    } else {
+        logsum += (t > 0.0) ? t * lnu : -t * lnd;
+    }
+}
+
+// dlog f / dtheta of a normsys entry (kind != THETA), branch-free
+__device__ __forceinline__ double hf_sf_dlog(int kind, const double* __restrict__ cf, double t) {
+    const double lnu = cf[0], lnd = cf[1];
+    if (kind == HF_SF_CODE4) {
+        double poly = cf[7], dpoly = 0.0;
+#pragma unroll
+        for (int i = 6; i >= 2; --i) {
+            dpoly = fma(dpoly, t, poly);
+            poly = fma(poly, t, cf[i]);
+        }
+        dpoly = fma(dpoly, t, poly);
+        poly = fma(poly, t, 1.0);
+        const double in = dpoly * __drcp_rn(poly);
+        return (t >= 1.0) ? lnu : ((t <= -1.0) ? -lnd : in);
+    }
+    return (t > 0.0) ? lnu : -lnd;
+}
+
 // main / constraint Poisson term without the theta-independent lgamma(n+1):
 // xlogy(n, lam) - lam   (tensor/numpy_backend.py:435-436)
 __host__ __device__ inline double hf_pois_term(double n, double lam) {
@@ -171,3 +227,12 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
                    int64_t B, double* out, double* grad, cudaStream_t st,
                    const int* row_idx = nullptr);
 int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out, cudaStream_t st);
+// DMMA main kernel (hf_eval_mma.cu); returns HF_ERR_UNSUPPORTED when the plan does not qualify
+int hf_main_mma_launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_point,
+                       const int* row_idx, bool grad, cudaStream_t st);
+static inline int hf_mma_ks(int H) {  // padded coefficient row stride, == 12 mod 16 doubles
+    int ks = 2 * H;
+    ks = (ks + HF_MMA_KC - 1) / HF_MMA_KC * HF_MMA_KC;
+    while (ks % 16 != 12) ++ks;
+    return ks;
+}
