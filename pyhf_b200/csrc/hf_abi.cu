@@ -118,6 +118,12 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
                 sfp_q[k] = q;
             }
     }
+    std::vector<int32_t> sfp_kind(NSF);
+    std::vector<double> sfp_coef((size_t)NSF * 8);
+    for (int k = 0; k < NSF; ++k) {
+        sfp_kind[k] = d->sf_kind[sfp_entry[k]];
+        for (int i = 0; i < 8; ++i) sfp_coef[(size_t)k * 8 + i] = d->sf_coef[(size_t)sfp_entry[k] * 8 + i];
+    }
     std::vector<int32_t> cons_kind(P, 0), cons_idx(P, 0);
     for (int i = 0; i < d->n_gauss; ++i) { cons_kind[d->g_par[i]] = 1; cons_idx[d->g_par[i]] = i; }
     for (int i = 0; i < d->n_pois; ++i) { cons_kind[d->p_par[i]] = 2; cons_idx[d->p_par[i]] = i; }
@@ -165,6 +171,8 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     const size_t o_sfpptr = pk.add(sfp_ptr.data(), sizeof(int32_t) * (P + 1));
     const size_t o_sfpent = pk.add(sfp_entry.data(), sizeof(int32_t) * NSF);
     const size_t o_sfpq = pk.add(sfp_q.data(), sizeof(int32_t) * NSF);
+    const size_t o_sfpkind = pk.add(sfp_kind.data(), sizeof(int32_t) * NSF);
+    const size_t o_sfpcoef = pk.add(sfp_coef.data(), sizeof(double) * 8 * NSF);
     const size_t o_bf = pk.add(d->bf_par, sizeof(int32_t) * (size_t)K * S * NB);
     const size_t o_gpar = pk.add(d->g_par, sizeof(int32_t) * d->n_gauss);
     const size_t o_gaux = pk.add(d->g_aux, sizeof(int32_t) * d->n_gauss);
@@ -197,9 +205,13 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     dp.t2t = DP(double, o_t2t); dp.sf_ptr = DP(int, o_sfptr); dp.sf_par = DP(int, o_sfpar);
     dp.sf_kind = DP(int, o_sfkind); dp.sf_coef = DP(double, o_sfcoef);
     dp.sfp_ptr = DP(int, o_sfpptr); dp.sfp_entry = DP(int, o_sfpent); dp.sfp_q = DP(int, o_sfpq);
+    dp.sfp_kind = DP(int, o_sfpkind); dp.sfp_coef = DP(double, o_sfpcoef);
     dp.bf_par = DP(int, o_bf); dp.g_par = DP(int, o_gpar); dp.g_aux = DP(int, o_gaux);
     dp.g_sigma = DP(double, o_gsig); dp.p_par = DP(int, o_ppar); dp.p_aux = DP(int, o_paux);
     dp.p_factor = DP(double, o_pfac); dp.par_cons_kind = DP(int, o_ck); dp.par_cons_idx = DP(int, o_ci);
+    dp.max_sf_q = 0; dp.max_sf_par = 0;
+    for (int q = 0; q < S * NSEG; ++q) dp.max_sf_q = std::max(dp.max_sf_q, d->sf_ptr[q + 1] - d->sf_ptr[q]);
+    for (int pp = 0; pp < P; ++pp) dp.max_sf_par = std::max(dp.max_sf_par, sfp_ptr[pp + 1] - sfp_ptr[pp]);
     dp.mma_ok = mma_ok ? 1 : 0; dp.mma_ntiles = mma_ntiles; dp.mma_nchunks = mma_nchunks;
     dp.mma_nother = n_other; dp.mma_other[0] = other[0]; dp.mma_other[1] = other[1];
     dp.mma_tt = DP(double, o_tt);

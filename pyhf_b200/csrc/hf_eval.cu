@@ -20,6 +20,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "hf_internal.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -46,33 +48,78 @@ __global__ void hf_transpose_pars_kernel(DevPlan pl, Work w, const double* __res
     }
 }
 
+constexpr int PREP_PPT = 4;  // points per thread: one coefficient fetch serves 4 evaluations
+
+constexpr int PREP_CAP = 256;  // entries staged per pass
+constexpr int FIN_CAP = 96;
+
 __global__ void hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
-    const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pt >= ld) return;
+    extern __shared__ __align__(16) double prep_smem[];
+    const int cap = min(max(pl.max_sf_q, 1), PREP_CAP);
+    double* cf_s = prep_smem;                                   // [cap][8]
+    int* kind_s = reinterpret_cast<int*>(cf_s + 8 * (size_t)cap);   // [cap]
+    int* par_s = kind_s + cap;                                  // [cap]
+    const int64_t base = (int64_t)blockIdx.x * blockDim.x * PREP_PPT + threadIdx.x;
+    int64_t pt[PREP_PPT];
+    bool ok[PREP_PPT];
+#pragma unroll
+    for (int i = 0; i < PREP_PPT; ++i) {
+        pt[i] = base + (int64_t)i * blockDim.x;
+        ok[i] = pt[i] < ld;
+        if (!ok[i]) pt[i] = ld - 1;
+    }
     // blockIdx.y strides over the work items: first H histosys modifiers, then S*NSEG products
     const int nq = pl.S * pl.NSEG;
     for (int item = blockIdx.y; item < pl.H + nq; item += gridDim.y) {
         if (item < pl.H) {
             const int h = item;
-            const double a = w.parsT[(int64_t)pl.hs_par[h] * ld + pt];
-            double c1, c2, d1, d2;
-            hf_hs_coeffs(pl.hs_code, a, c1, c2, d1, d2);
-            w.c1T[(int64_t)h * ld + pt] = c1;
-            w.c2T[(int64_t)h * ld + pt] = c2;
-            if (do_grad) {
-                w.dc1T[(int64_t)h * ld + pt] = d1;
-                w.dc2T[(int64_t)h * ld + pt] = d2;
+#pragma unroll
+            for (int i = 0; i < PREP_PPT; ++i) {
+                if (!ok[i]) continue;
+                const double a = w.parsT[(int64_t)pl.hs_par[h] * ld + pt[i]];
+                double c1, c2, d1, d2;
+                hf_hs_coeffs(pl.hs_code, a, c1, c2, d1, d2);
+                w.c1T[(int64_t)h * ld + pt[i]] = c1;
+                w.c2T[(int64_t)h * ld + pt[i]] = c2;
+                if (do_grad) {
+                    w.dc1T[(int64_t)h * ld + pt[i]] = d1;
+                    w.dc2T[(int64_t)h * ld + pt[i]] = d2;
+                }
             }
         } else {
             const int q = item - pl.H;
-            double prod = 1.0, logsum = 0.0;
-            const int e1 = pl.sf_ptr[q + 1];
-            for (int e = pl.sf_ptr[q]; e < e1; ++e) {
-                const double t = w.parsT[(int64_t)pl.sf_par[e] * ld + pt];
-                hf_sf_accum(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, t, prod, logsum);
+            double prod[PREP_PPT], logsum[PREP_PPT];
+#pragma unroll
+            for (int i = 0; i < PREP_PPT; ++i) { prod[i] = 1.0; logsum[i] = 0.0; }
+            // the entry table of this (sample, segment) goes through shared memory: the
+            // coefficient stream (0.5 MB on C4) does not survive in L1 next to the parameter rows
+            for (int e0 = pl.sf_ptr[q]; e0 < pl.sf_ptr[q + 1]; e0 += cap) {
+            const int ne = min(cap, pl.sf_ptr[q + 1] - e0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < ne * 8; i += blockDim.x) cf_s[i] = pl.sf_coef[8 * (int64_t)e0 + i];
+            for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+                kind_s[i] = pl.sf_kind[e0 + i];
+                par_s[i] = pl.sf_par[e0 + i];
             }
-            if (logsum != 0.0) prod *= exp(logsum);
-            w.FsegT[(int64_t)q * ld + pt] = prod;
+            __syncthreads();
+            for (int e = 0; e < ne; ++e) {
+                const int kind = kind_s[e];
+                const int64_t prow = (int64_t)par_s[e] * ld;
+                double cf[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) cf[c] = cf_s[8 * e + c];
+#pragma unroll
+                for (int i = 0; i < PREP_PPT; ++i)
+                    hf_sf_accum(kind, cf, w.parsT[prow + pt[i]], prod[i], logsum[i]);
+            }
+            }
+#pragma unroll
+            for (int i = 0; i < PREP_PPT; ++i) {
+                if (!ok[i]) continue;
+                double v = prod[i];
+                if (logsum[i] != 0.0) v *= exp(logsum[i]);
+                w.FsegT[(int64_t)q * ld + pt[i]] = v;
+            }
         }
     }
 }
@@ -411,64 +458,110 @@ __global__ void hf_finish_value_kernel(DevPlan pl, Work w, int64_t B, int64_t ld
     out[pt] = acc;
 }
 
+constexpr int FIN_PPT = 4;  // points per thread in hf_finish_grad_kernel
+
 __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                                       const double* __restrict__ data, int per_point,
                                       const int* __restrict__ row_idx, double* __restrict__ grad) {
-    // 32 points x 32 parameters per block; transposed through shared memory so that both the
-    // batch-major reads and the row-major writes coalesce
-    __shared__ double tile[32][33];
-    const int64_t pt0 = (int64_t)blockIdx.x * 32;
+    // 128 points x 32 parameters per block; every thread carries 4 points so that one fetch of an
+    // entry's coefficients serves 4 evaluations; transposed through shared memory so that both
+    // the batch-major reads and the row-major writes coalesce
+    __shared__ double tile[32][32 * FIN_PPT + 1];
+    extern __shared__ __align__(16) double fin_smem[];
+    // per-warp staging of one parameter's entry table: [8 warps][max_sf_par] x (8 coef, kind, q)
+    const int cap = min(max(pl.max_sf_par, 1), FIN_CAP);
+    double* cf_w = fin_smem + (size_t)threadIdx.y * cap * 8;
+    int* kind_w = reinterpret_cast<int*>(fin_smem + (size_t)8 * cap * 8) + (size_t)threadIdx.y * cap * 2;
+    int* q_w = kind_w + cap;
+    const int64_t pt0 = (int64_t)blockIdx.x * 32 * FIN_PPT;
     const int p0 = blockIdx.y * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
     for (int j = ty; j < 32; j += 8) {
         const int p = p0 + j;
-        const int64_t pt = pt0 + tx;
-        double g = 0.0;
-        if (p < pl.P && pt < B) {
-            g = w.gradT[(int64_t)p * ld + pt];
-            const double th = w.parsT[(int64_t)p * ld + pt];
+        double g[FIN_PPT], th[FIN_PPT];
+        int64_t pt[FIN_PPT];
+        bool ok[FIN_PPT];
+#pragma unroll
+        for (int i = 0; i < FIN_PPT; ++i) {
+            pt[i] = pt0 + tx + 32 * i;
+            ok[i] = p < pl.P && pt[i] < B;
+            if (pt[i] >= B) pt[i] = B - 1;
+            g[i] = ok[i] ? w.gradT[(int64_t)p * ld + pt[i]] : 0.0;
+            th[i] = (p < pl.P) ? w.parsT[(int64_t)p * ld + pt[i]] : 1.0;
+        }
+        if (p < pl.P) {
             // scalar factors (normsys / normfactor / lumi): sum_e (dF_q/dtheta) * G_q with
             // dF_q/dtheta = dlog f_e * F_q, or the product of the *other* factors of q for a
             // plain theta factor (finite at theta == 0: the POI sits on its bound in q~ fits)
-            const int e1 = pl.sfp_ptr[p + 1];
-            for (int k = pl.sfp_ptr[p]; k < e1; ++k) {
-                const int e = pl.sfp_entry[k];
-                const int q = pl.sfp_q[k];
-                double coef;
-                if (pl.sf_kind[e] == HF_SF_THETA) {
-                    double logsum = 0.0;
-                    coef = 1.0;
-                    for (int e2 = pl.sf_ptr[q]; e2 < pl.sf_ptr[q + 1]; ++e2) {
-                        if (e2 == e) continue;
-                        hf_sf_accum(pl.sf_kind[e2], pl.sf_coef + 8 * (int64_t)e2,
-                                    w.parsT[(int64_t)pl.sf_par[e2] * ld + pt], coef, logsum);
-                    }
-                    if (logsum != 0.0) coef *= exp(logsum);
-                } else {
-                    coef = hf_sf_dlog(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, th) *
-                           w.FsegT[(int64_t)q * ld + pt];
+            const int k0 = pl.sfp_ptr[p], e1 = pl.sfp_ptr[p + 1];
+            if (k0 < e1 && pl.sfp_kind[k0] != HF_SF_THETA) {
+                for (int kc = k0; kc < e1; kc += cap) {
+                const int ne = min(cap, e1 - kc);
+                __syncwarp();
+                for (int i = tx; i < ne * 8; i += 32) cf_w[i] = pl.sfp_coef[8 * (int64_t)kc + i];
+                for (int i = tx; i < ne; i += 32) {
+                    kind_w[i] = pl.sfp_kind[kc + i];
+                    q_w[i] = pl.sfp_q[kc + i];
                 }
-                g = fma(coef, w.GsegT[(int64_t)q * ld + pt], g);
+                __syncwarp();
+                for (int k = 0; k < ne; ++k) {
+                    const int kind = kind_w[k];
+                    const int64_t qrow = (int64_t)q_w[k] * ld;
+                    double cf[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) cf[c] = cf_w[8 * k + c];
+#pragma unroll
+                    for (int i = 0; i < FIN_PPT; ++i)
+                        g[i] = fma(hf_sf_dlog(kind, cf, th[i]), w.FsegT[qrow + pt[i]] * w.GsegT[qrow + pt[i]], g[i]);
+                }
+                }
+            } else {
+                for (int k = k0; k < e1; ++k) {
+                    const int e = pl.sfp_entry[k];
+                    const int q = pl.sfp_q[k];
+#pragma unroll
+                    for (int i = 0; i < FIN_PPT; ++i) {
+                        double coef;
+                        if (pl.sf_kind[e] == HF_SF_THETA) {
+                            double logsum = 0.0;
+                            coef = 1.0;
+                            for (int e2 = pl.sf_ptr[q]; e2 < pl.sf_ptr[q + 1]; ++e2) {
+                                if (e2 == e) continue;
+                                hf_sf_accum(pl.sf_kind[e2], pl.sf_coef + 8 * (int64_t)e2,
+                                            w.parsT[(int64_t)pl.sf_par[e2] * ld + pt[i]], coef, logsum);
+                            }
+                            if (logsum != 0.0) coef *= exp(logsum);
+                        } else {
+                            coef = hf_sf_dlog(pl.sf_kind[e], pl.sf_coef + 8 * (int64_t)e, th[i]) *
+                                   w.FsegT[(int64_t)q * ld + pt[i]];
+                        }
+                        g[i] = fma(coef, w.GsegT[(int64_t)q * ld + pt[i]], g[i]);
+                    }
+                }
             }
             const int ck = pl.par_cons_kind[p];
-            if (ck == 1) {
-                const int i = pl.par_cons_idx[p];
-                const double sg = pl.g_sigma[i];
-                const int64_t row = hf_row_of(row_idx, per_point, pt);
-                g += (data[row * pl.D + pl.NB + pl.g_aux[i]] - th) / (sg * sg);
-            } else if (ck == 2) {
-                const int i = pl.par_cons_idx[p];
-                const int64_t row = hf_row_of(row_idx, per_point, pt);
-                g += data[row * pl.D + pl.NB + pl.p_aux[i]] / th - pl.p_factor[i];
+            if (ck != 0) {
+                const int ci = pl.par_cons_idx[p];
+#pragma unroll
+                for (int i = 0; i < FIN_PPT; ++i) {
+                    const int64_t row = hf_row_of(row_idx, per_point, pt[i]);
+                    if (ck == 1) {
+                        const double sg = pl.g_sigma[ci];
+                        g[i] += (data[row * pl.D + pl.NB + pl.g_aux[ci]] - th[i]) / (sg * sg);
+                    } else {
+                        g[i] += data[row * pl.D + pl.NB + pl.p_aux[ci]] / th[i] - pl.p_factor[ci];
+                    }
+                }
             }
         }
-        tile[j][tx] = g;
+#pragma unroll
+        for (int i = 0; i < FIN_PPT; ++i) tile[j][tx + 32 * i] = g[i];
     }
     __syncthreads();
-    for (int j = ty; j < 32; j += 8) {
-        const int64_t pt = pt0 + j;
+    for (int r = ty; r < 32 * FIN_PPT; r += 8) {
+        const int64_t pt = pt0 + r;
         const int p = p0 + tx;
-        if (p < pl.P && pt < B) grad[pt * pl.P + p] = tile[tx][j];
+        if (p < pl.P && pt < B) grad[pt * pl.P + p] = tile[tx][r];
     }
 }
 
@@ -601,8 +694,8 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
     {
         const int items = pl.H + pl.S * pl.NSEG;
         int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
-        dim3 grid((unsigned)((ld + 127) / 128), (unsigned)gy);
-        hf_prep_kernel<<<grid, 128, 0, st>>>(pl, w, ld, do_grad ? 1 : 0);
+        dim3 grid((unsigned)((ld + 128 * PREP_PPT - 1) / (128 * PREP_PPT)), (unsigned)gy);
+        hf_prep_kernel<<<grid, 128, (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, do_grad ? 1 : 0);
         plan->launches++;
     }
     HF_CUDA_OK(cudaMemsetAsync(w.mainv, 0, sizeof(double) * ld, st));
@@ -649,8 +742,10 @@ finish:
                                                                         row_idx, out);
     plan->launches++;
     if (do_grad) {
-        dim3 grid((unsigned)((B + 31) / 32), (unsigned)((pl.P + 31) / 32));
-        hf_finish_grad_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, B, ld, data, per_point, row_idx, grad);
+        dim3 grid((unsigned)((B + 32 * FIN_PPT - 1) / (32 * FIN_PPT)), (unsigned)((pl.P + 31) / 32));
+        const size_t fin_smem = (size_t)std::min(std::max(pl.max_sf_par, 1), FIN_CAP) * (8 * 72) + 16;
+        HF_CUDA_OK(cudaFuncSetAttribute(hf_finish_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        hf_finish_grad_kernel<<<grid, dim3(32, 8), fin_smem, st>>>(pl, w, B, ld, data, per_point, row_idx, grad);
         plan->launches++;
     }
     HF_CUDA_OK(cudaGetLastError());
@@ -668,7 +763,8 @@ int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out
     hf_transpose_pars_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, pars, B, ld);
     const int items = pl.H + pl.S * pl.NSEG;
     int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
-    hf_prep_kernel<<<dim3((unsigned)((ld + 127) / 128), (unsigned)gy), 128, 0, st>>>(pl, w, ld, 0);
+    hf_prep_kernel<<<dim3((unsigned)((ld + 128 * PREP_PPT - 1) / (128 * PREP_PPT)), (unsigned)gy), 128,
+                     (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, 0);
     const int64_t n = B * pl.D;
     hf_expected_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl, w, B, ld, out);
     plan->launches += 3;

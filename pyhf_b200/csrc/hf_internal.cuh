@@ -30,6 +30,8 @@ struct DevPlan {
     const int* sfp_ptr;          // [P+1]   by-parameter CSR of scalar-factor entries
     const int* sfp_entry;        // [NSF]   entry index
     const int* sfp_q;            // [NSF]   q = sample*NSEG+seg of that entry
+    const int* sfp_kind;         // [NSF]   kind, in by-parameter order
+    const double* sfp_coef;      // [NSF][8] coefficients, in by-parameter order
     const int* bf_par;           // [K][S][NB]
     const int* g_par;            // [NG]
     const int* g_aux;            // [NG]
@@ -40,6 +42,7 @@ struct DevPlan {
     const int* par_cons_kind;    // [P] 0 none, 1 gauss, 2 poisson
     const int* par_cons_idx;     // [P] index into g_* / p_*
     // ---- DMMA path (hf_eval_mma.cu): tables re-tiled for bulk copies into shared memory
+    int max_sf_q, max_sf_par;    // longest scalar-factor entry list per (sample, segment) / per parameter
     int mma_ok;                  // plan fits the tensor-core kernel (0 < H, R <= 4, <= 2 other samples)
     int mma_ntiles;              // bin tiles of HF_MMA_BT bins
     int mma_nchunks;             // K chunks of HF_MMA_KC columns (column 2h = T1_h, 2h+1 = T2_h)
