@@ -38,6 +38,8 @@ struct FitDev {
     // per-fit state
     double *X, *G, *Dd, *XT, *GT, *VT, *F, *T, *EDM, *EDMPREV, *H, *Hshared;
     int *done, *need_dir, *own, *status, *niter, *refresh, *rlist, *counters;
+    int *nfail, *force, *rlist2;  // consecutive rejections, (unused), second request list
+    double* damp;                 // Levenberg-Marquardt damping added to the diagonal (0 = pure Newton)
     int *live, *live_next;   // compacted list of fits still running (order is arbitrary)
     const int* islocal;      // [P] 1 when the parameter only couples to the global block (diagonal local block)
     int use_local;           // structured Cholesky: local parameters first, their block is diagonal
@@ -69,6 +71,7 @@ __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64
     if (p == 0) {
         s.done[i] = 0; s.need_dir[i] = 1; s.own[i] = 0; s.status[i] = 1; s.niter[i] = 0;
         s.refresh[i] = 0; s.T[i] = 1.0; s.EDM[i] = INFINITY; s.EDMPREV[i] = INFINITY;
+        s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = 0.0;
     }
 }
 
@@ -270,7 +273,7 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     for (int k = 0; k < nth / 32; ++k) maxdiag = fmax(maxdiag, s_red[k]);
     __syncthreads();
 
-    double tau = 0.0;
+    double tau = s.damp[toy];  // Levenberg-Marquardt damping carried by the fit (0 = pure Newton)
     bool ok = false;
     for (int attempt = 0; attempt < 40 && !ok; ++attempt) {
         // rows of the packed lower triangle; off-diagonal entries of the local block are never
@@ -283,7 +286,7 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
         }
         __syncthreads();
         ok = chol_factor(A, n, nloc, tid, nth);
-        if (!ok) tau = (tau == 0.0) ? 1e-8 * fmax(maxdiag, 1e-300) : tau * 10.0;
+        if (!ok) tau = (tau < 1e-8 * maxdiag) ? 1e-8 * fmax(maxdiag, 1e-300) : tau * 10.0;
     }
     if (!ok) {
         if (tid == 0) { s.done[toy] = 1; s.status[toy] = 2; }
@@ -338,16 +341,33 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     edm = 0.0; step = 0.0;
     for (int k = 0; k < nth / 32; ++k) { edm += s_red[k]; step = fmax(step, s_red2[k]); }
 
-    if (allow_refresh) {
+    if (allow_refresh == 1) {
         const bool slow = edm > s.refresh_ratio * s.EDMPREV[toy];
-        const bool want = s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm;
+        const bool forced = s.force[toy] != 0;
+        const bool fresh = s.need_dir[toy] == 1;  // 2 = same point, damping raised after a rejection
+        const bool want = fresh && (forced || (s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm));
         if (want) {
             if (tid == 0) {
-                s.refresh[toy] = (edm < s.exact_below) ? 2 : 1;
+                // exact Hessian close to the minimum, Fisher matrix (PSD) far from it or after a
+                // failed line search
+                s.refresh[toy] = (!forced && edm < s.exact_below) ? 2 : 1;
+                s.force[toy] = 0;
+                s.EDM[toy] = edm;  // estimate before the refresh (checked after it)
                 const int k = atomicAdd(&s.counters[0], 1);
                 s.rlist[k] = (int)toy;
             }
             return;  // need_dir stays set: the direction is recomputed after the refresh
+        }
+    } else if (allow_refresh == 0) {
+        // after an EXACT refresh: a nearly singular / indefinite exact Hessian shows up as an
+        // exploding step; fall back to the Fisher matrix for this iteration
+        if (s.refresh[toy] == 2 && (!(edm <= 100.0 * s.EDM[toy] + 1.0) || step > 100.0)) {
+            if (tid == 0) {
+                s.refresh[toy] = 1;
+                const int k = atomicAdd(&s.counters[2], 1);
+                s.rlist2[k] = (int)toy;
+            }
+            return;
         }
     }
     double* d = s.Dd + toy * P;
@@ -414,18 +434,26 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
         if (lane == 0) {
             s.F[toy] = ft;
             s.need_dir[toy] = 1;
+            s.nfail[toy] = 0;
+            const double dmp = 0.2 * s.damp[toy];
+            s.damp[toy] = (dmp < 1e-6) ? 0.0 : dmp;
             const int it = s.niter[toy] + 1;
             s.niter[toy] = it;
             if (it >= s.max_iter) { s.done[toy] = 1; s.status[toy] = 1; alive = false; }
         }
     } else if (lane == 0) {
-        const double t = s.T[toy];
-        if (t < 1e-4) {
-            s.done[toy] = 1;
-            s.status[toy] = (s.EDM[toy] < 1e-7) ? 0 : 2;
-            alive = false;
+        // rejected: raise the damping and recompute the direction at the same point (trust-region
+        // style) instead of shrinking the step along a direction a nearly singular Hessian made bad
+        const int nr = s.nfail[toy] + 1;
+        if (s.EDM[toy] < 1e-7) {  // predicted decrease below the rounding floor of f: converged
+            s.done[toy] = 1; s.status[toy] = 0; alive = false;
+        } else if (nr > 60) {
+            s.done[toy] = 1; s.status[toy] = 2; alive = false;
         } else {
-            s.T[toy] = 0.5 * t;
+            const double dmp = s.damp[toy];
+            s.damp[toy] = fmax(8.0 * dmp, 1e-2);
+            s.nfail[toy] = nr;
+            s.need_dir[toy] = 2;
         }
     }
     if (lane == 0 && alive) live_next[atomicAdd(&s.counters[1], 1)] = (int)toy;
@@ -563,6 +591,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.status = c.take<int>(NC); s.niter = c.take<int>(NC); s.refresh = c.take<int>(NC);
         s.rlist = c.take<int>(NC + 1); s.counters = c.take<int>(8);
         s.live = c.take<int>(NC + 1); s.live_next = c.take<int>(NC + 1);
+        s.nfail = c.take<int>(NC); s.force = c.take<int>(NC); s.rlist2 = c.take<int>(NC + 1);
+        s.damp = c.take<double>(NC);
         d_islocal = c.take<int>(P);
         XP = c.take<double>((size_t)max_pts * P); GP = c.take<double>((size_t)max_pts * P);
         VP = c.take<double>(max_pts); DR = c.take<double>((size_t)rl_cap * D);
@@ -699,6 +729,20 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                     fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, s.rlist + i0, nb, 0);
                     plan->launches++;
                     if (!chol_in_smem) HF_CUDA_OK(cudaStreamSynchronize(st));
+                }
+                // fits whose exact Hessian turned out unusable: Fisher matrix instead
+                HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+                HF_CUDA_OK(cudaStreamSynchronize(st));
+                const int nfall = h_counters[2];
+                if (nfall > 0) {
+                    rc = run_hessians(s.rlist2, nfall, s.refresh, toy0, 0);
+                    if (rc) return rc;
+                    for (int64_t i0 = 0; i0 < nfall; i0 += dir_step) {
+                        const int64_t nb = std::min<int64_t>(dir_step, nfall - i0);
+                        fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, s.rlist2 + i0, nb, -1);
+                        plan->launches++;
+                        if (!chol_in_smem) HF_CUDA_OK(cudaStreamSynchronize(st));
+                    }
                 }
             }
             if (prof) { double t1 = tick(); t_dir2 += t1 - t0; t0 = t1; }
