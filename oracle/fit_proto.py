@@ -9,7 +9,10 @@ gradient (a batch of perturbed points through the same logpdf+grad kernel):
     decrease stops shrinking fast enough (modified Newton in between).
 
 Bounds: active-set projection (a variable on a bound whose gradient pushes outward is frozen for
-the step), projected backtracking line search with an Armijo test.
+the step).  Globalisation: Levenberg-Marquardt -- a rejected trial (Armijo test on the projected
+step) raises a per-fit damping added to the Hessian diagonal and the direction is recomputed at
+the same point; accepted steps relax it.  (Plain backtracking failed on ~1e-4 of the C3 toys whose
+exact Hessian is nearly singular along a degenerate normsys direction.)
 
 The CUDA implementation (pyhf_b200/csrc/hf_fit.cu + the host loop in pyhf_b200/fit.py) is a
 transcription of this file; tests compare both against the reference's scipy SLSQP results.
@@ -36,9 +39,10 @@ def fd_hessian(pl, x, data, free, g0=None, h=1e-5):
     return Hm
 
 
-def solve_reduced(Hm, g, act):
+def solve_reduced(Hm, g, act, damp=None):
     """Newton direction on the non-active variables: (H_FF + tau I) d = -g_F, d_A = 0.
-    tau grows until the Cholesky factorisation succeeds (modified Newton)."""
+    tau starts at the fit's Levenberg-Marquardt damping and grows until the Cholesky
+    factorisation succeeds (modified Newton)."""
     N, P = g.shape
     d = np.zeros((N, P))
     edm = np.zeros(N)
@@ -47,7 +51,7 @@ def solve_reduced(Hm, g, act):
         if not len(f):
             continue
         A = Hm[i][np.ix_(f, f)]
-        tau = 0.0
+        tau = 0.0 if damp is None else float(damp[i])
         scale = max(np.max(np.abs(np.diag(A))), 1e-300)
         for _ in range(60):
             try:
@@ -88,7 +92,9 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
     status = np.full(N, 1)
     niter = np.zeros(N, int)
     done = np.zeros(N, bool)
-    t = np.ones(N)
+    damp = np.zeros(N)
+    nrej = np.zeros(N, int)
+    fresh = np.ones(N, bool)   # direction needed after an ACCEPTED step (curvature may refresh)
     d = np.zeros((N, P))
     need_dir = np.ones(N, bool)
     edm_prev = np.full(N, np.inf)
@@ -99,11 +105,11 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
         if len(rows):
             xr, gr = x[rows], g[rows]
             act = fixed[None, :] | ((xr <= lo) & (gr > 0)) | ((xr >= hi) & (gr < 0))
-            dd, edm = solve_reduced(Hm[rows], gr, act)
+            dd, edm = solve_reduced(Hm[rows], gr, act, damp[rows])
             # curvature refresh: first own Hessian after the start-up step, later when the
             # predicted decrease did not shrink by 1/refresh_ratio
             slow = edm > refresh_ratio * edm_prev[rows]
-            refresh = (niter[rows] >= 1) & (~own[rows] | slow) & (edm > tol_edm)
+            refresh = fresh[rows] & (niter[rows] >= 1) & (~own[rows] | slow) & (edm > tol_edm)
             if np.any(refresh):
                 rr = rows[refresh]
                 # far from the minimum the exact Hessian is often indefinite (log-sum-exp of the
@@ -116,7 +122,16 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
                 Hm[rr] = fd_hessian(pl, x[rr], dd_rows, free)
                 own[rr] = True
                 n_hess += len(rr)
-                dd2, edm2 = solve_reduced(Hm[rr], g[rr], act[refresh])
+                dd2, edm2 = solve_reduced(Hm[rr], g[rr], act[refresh], damp[rr])
+                # a nearly singular / indefinite exact Hessian shows up as an exploding step:
+                # fall back to the Fisher matrix for this iteration
+                blow = exact & (~(edm2 <= 100.0 * edm[refresh] + 1.0) | (np.max(np.abs(dd2), axis=1) > 100.0))
+                if np.any(blow):
+                    rb = rr[blow]
+                    Hm[rb] = fd_hessian(pl, x[rb], O.expected_data(pl, x[rb]), free)
+                    n_hess += len(rb)
+                    dd3, edm3 = solve_reduced(Hm[rb], g[rb], act[refresh][blow], damp[rb])
+                    dd2[blow], edm2[blow] = dd3, edm3
                 dd[refresh], edm[refresh] = dd2, edm2
             step = np.max(np.abs(dd), axis=1)
             conv = (edm < tol_edm) & (step < tol_step)
@@ -125,27 +140,37 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
             done[rows[conv]] = True
             status[rows[conv]] = 0
             d[rows] = dd
-            t[rows] = 1.0
             need_dir[rows] = False
             if verbose:
                 print(it, "edm", edm[:4], "f", f[rows][:4], "refresh", refresh[:4])
         live = np.nonzero(~done)[0]
         if not len(live):
             break
-        xt = np.clip(x[live] + t[live, None] * d[live], lo, hi)
+        xt = np.clip(x[live] + d[live], lo, hi)
         ft, gt = fg(xt, live)
         nevals += 1
         dec = np.einsum("ij,ij->i", g[live], xt - x[live])
         slack = 4e-15 * np.maximum(1.0, np.abs(f[live]))
         ok = np.isfinite(ft) & (ft <= f[live] + 1e-4 * dec + slack)
-        stall = t[live] < 1e-4
         acc = live[ok]
         x[acc], f[acc], g[acc] = xt[ok], ft[ok], gt[ok]
         need_dir[acc] = True
+        fresh[acc] = True
         niter[acc] += 1
+        nrej[acc] = 0
+        damp[acc] = np.where(0.2 * damp[acc] < 1e-6, 0.0, 0.2 * damp[acc])
         rej = live[~ok]
-        t[rej] *= 0.5
-        dead = live[stall & ~ok]
+        # rejected: converged if the predicted decrease is below the rounding floor of f,
+        # otherwise raise the damping and recompute the direction at the same point
+        floor = edm_last[rej] < 1e-7
+        done[rej[floor]] = True
+        status[rej[floor]] = 0
+        rej = rej[~floor]
+        nrej[rej] += 1
+        dead = rej[nrej[rej] > 60]
         done[dead] = True
-        status[dead] = np.where(edm_last[dead] < 1e-7, 0, 2)
+        status[dead] = 2
+        damp[rej] = np.maximum(8.0 * damp[rej], 1e-2)
+        need_dir[rej] = True
+        fresh[rej] = False
     return x, f, status, niter, dict(rounds=nevals, hessians=n_hess)

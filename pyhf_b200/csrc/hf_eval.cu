@@ -458,11 +458,12 @@ __global__ void hf_finish_value_kernel(DevPlan pl, Work w, int64_t B, int64_t ld
     out[pt] = acc;
 }
 
-constexpr int FIN_PPT = 4;  // points per thread in hf_finish_grad_kernel
+constexpr int FIN_PPT = 2;  // points per thread in hf_finish_grad_kernel
 
 __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                                       const double* __restrict__ data, int per_point,
-                                      const int* __restrict__ row_idx, double* __restrict__ grad) {
+                                      const int* __restrict__ row_idx, double* __restrict__ grad,
+                                      int x_in_smem) {
     // 128 points x 32 parameters per block; every thread carries 4 points so that one fetch of an
     // entry's coefficients serves 4 evaluations; transposed through shared memory so that both
     // the batch-major reads and the row-major writes coalesce
@@ -476,6 +477,22 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
     const int64_t pt0 = (int64_t)blockIdx.x * 32 * FIN_PPT;
     const int p0 = blockIdx.y * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    // X_q = F_q * G_q of the block's points, staged once: every parameter of the block walks the
+    // same S*NSEG rows, which would otherwise be re-fetched from L2 for each of its entries
+    constexpr int NPB = 32 * FIN_PPT;
+    double* xs = fin_smem + (size_t)8 * cap * 9;  // behind the per-warp entry tables
+    if (x_in_smem) {
+        const int nq = pl.S * pl.NSEG;
+        for (int q = ty; q < nq; q += 8) {
+#pragma unroll
+            for (int i = 0; i < FIN_PPT; ++i) {
+                int64_t pt = pt0 + tx + 32 * i;
+                if (pt >= B) pt = B - 1;
+                xs[(size_t)q * NPB + tx + 32 * i] = w.FsegT[(int64_t)q * ld + pt] * w.GsegT[(int64_t)q * ld + pt];
+            }
+        }
+        __syncthreads();
+    }
     for (int j = ty; j < 32; j += 8) {
         const int p = p0 + j;
         double g[FIN_PPT], th[FIN_PPT];
@@ -506,13 +523,21 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                 __syncwarp();
                 for (int k = 0; k < ne; ++k) {
                     const int kind = kind_w[k];
-                    const int64_t qrow = (int64_t)q_w[k] * ld;
+                    const int q = q_w[k];
                     double cf[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) cf[c] = cf_w[8 * k + c];
+                    if (x_in_smem) {
 #pragma unroll
-                    for (int i = 0; i < FIN_PPT; ++i)
-                        g[i] = fma(hf_sf_dlog(kind, cf, th[i]), w.FsegT[qrow + pt[i]] * w.GsegT[qrow + pt[i]], g[i]);
+                        for (int i = 0; i < FIN_PPT; ++i)
+                            g[i] = fma(hf_sf_dlog(kind, cf, th[i]), xs[(size_t)q * NPB + tx + 32 * i], g[i]);
+                    } else {
+                        const int64_t qrow = (int64_t)q * ld;
+#pragma unroll
+                        for (int i = 0; i < FIN_PPT; ++i)
+                            g[i] = fma(hf_sf_dlog(kind, cf, th[i]),
+                                       w.FsegT[qrow + pt[i]] * w.GsegT[qrow + pt[i]], g[i]);
+                    }
                 }
                 }
             } else {
@@ -743,9 +768,12 @@ finish:
     plan->launches++;
     if (do_grad) {
         dim3 grid((unsigned)((B + 32 * FIN_PPT - 1) / (32 * FIN_PPT)), (unsigned)((pl.P + 31) / 32));
-        const size_t fin_smem = (size_t)std::min(std::max(pl.max_sf_par, 1), FIN_CAP) * (8 * 72) + 16;
+        size_t fin_smem = (size_t)std::min(std::max(pl.max_sf_par, 1), FIN_CAP) * (8 * 72) + 16;
+        const size_t xs_bytes = sizeof(double) * (size_t)pl.S * pl.NSEG * 32 * FIN_PPT;
+        const int x_in_smem = (fin_smem + xs_bytes <= 150 * 1024) ? 1 : 0;
+        if (x_in_smem) fin_smem += xs_bytes;
         HF_CUDA_OK(cudaFuncSetAttribute(hf_finish_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-        hf_finish_grad_kernel<<<grid, dim3(32, 8), fin_smem, st>>>(pl, w, B, ld, data, per_point, row_idx, grad);
+        hf_finish_grad_kernel<<<grid, dim3(32, 8), fin_smem, st>>>(pl, w, B, ld, data, per_point, row_idx, grad, x_in_smem);
         plan->launches++;
     }
     HF_CUDA_OK(cudaGetLastError());
