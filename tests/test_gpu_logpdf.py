@@ -169,3 +169,39 @@ def test_host_buffer_entry_point(golden, cuda):
     assert np.allclose(out.numpy(), g["logpdf"], rtol=RTOL, atol=0)
     scale = np.max(np.abs(g["grad"]), axis=1, keepdims=True)
     assert (np.abs(grad.numpy() - g["grad"]) / scale).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["mixed_code4p_code4", "mixed_code0_code1", "val_2bin_histosys",
+                                  "val_2bin_2channel_coupledhistosys"])
+@pytest.mark.parametrize("B", [256, 1000])
+def test_tensor_core_path_on_small_models(name, B, golden, cuda, monkeypatch):
+    """B >= 256 routes histosys models through hf_main_mma_kernel (DMMA + bulk-copy staging):
+    padded histosys rows (R < 4), a single K chunk, several per-bin factors per cell, code0,
+    ragged last point tile, per-point data; checked against the vector-FMA kernel and the oracle"""
+    from oracle import hf_oracle as O
+
+    g = golden(name)
+    hp, op = g.host_plan(), g.oracle_plan()
+    assert hp.n_hs > 0
+    plan = _dev_plan(g, cuda)
+    rng = np.random.default_rng(B)
+    width = np.minimum(0.05 * (hp.hi - hp.lo), 0.6)
+    pars = hp.init[None] + rng.normal(0, 1, (B, hp.n_pars)) * width[None]
+    pars = np.clip(pars, hp.lo + 0.05, hp.hi)
+    pars[:, hp.fixed.astype(bool)] = hp.init[hp.fixed.astype(bool)]
+    pars[0, hp.poi_index] = hp.lo[hp.poi_index]
+    lam = O.expected_data(op, pars)
+    data = np.where(np.arange(lam.shape[1])[None] < hp.n_bins, rng.poisson(np.maximum(lam, 0)), lam).astype(float)
+    monkeypatch.setenv("HF_MMA", "1")
+    v1, g1 = plan.logpdf_grad(pars, data)
+    v1s = plan.logpdf(pars, data[0])
+    monkeypatch.setenv("HF_MMA", "0")
+    v0, g0 = plan.logpdf_grad(pars, data)
+    v0s = plan.logpdf(pars, data[0])
+    v_ref, g_ref = O.logpdf_grad(op, pars, data)
+    for v, gr in ((v1, g1), (v0, g0)):
+        v, gr = v.cpu().numpy(), gr.cpu().numpy()
+        assert np.allclose(v, v_ref, rtol=1e-11, atol=1e-10), np.abs(v - v_ref).max()
+        sc = np.max(np.abs(g_ref), axis=1, keepdims=True) + 1e-300
+        assert (np.abs(gr - g_ref) / sc).max() < 1e-10
+    assert torch.allclose(v1s, v0s, rtol=1e-12, atol=1e-10)
