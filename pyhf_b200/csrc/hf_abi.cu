@@ -135,7 +135,7 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
             if (n_other < 2) other[n_other] = s;
             ++n_other;
         }
-    const bool mma_ok = H > 0 && R <= 4 && S <= 8;
+    const bool mma_ok = H > 0 && R <= 4 && n_other <= 4 && !d->has_clip_sample && !d->has_clip_bin;
     const int mma_ntiles = (NB + HF_MMA_BT - 1) / HF_MMA_BT;
     const int mma_nchunks = (2 * H + HF_MMA_KC - 1) / HF_MMA_KC;
     std::vector<double> tt;

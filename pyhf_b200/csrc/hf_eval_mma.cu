@@ -94,7 +94,7 @@ __device__ __forceinline__ void cell_bf_grad(const DevPlan& pl, const Work& w, i
 constexpr int SMAX = 8;  // samples handled by the register-resident per-(sample, segment) sums
 constexpr int NTHR = 256;  // 8 warps: forward = 16 cells each, backward = (8 points) x (64 cells) each
 
-template <int NCH, bool GRAD>
+template <int NCH, bool GRAD, bool HASBF>
 __global__ void __launch_bounds__(NTHR, 1)
 hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
                    int per_point, const int* __restrict__ row_idx, int KS) {
@@ -108,7 +108,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     double* nom_s = nd_s + MM * (BT + 1);                            // [S][BT]    nominal of the tile
     int* seg_s = reinterpret_cast<int*>(nom_s + SMAX * BT);          // [BT]
     int* srow_s = seg_s + BT;                                        // [SMAX]     histosys row of a sample
-    int* bf_s = srow_s + SMAX;                                       // [K][S][BT] per-bin factor indices
+    int* bfany_s = srow_s + SMAX;                                    // [BT]  bin carries a per-bin factor
+    int* bf_s = bfany_s + BT;                                        // [K][S][BT] per-bin factor indices
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int64_t pt0 = (int64_t)blockIdx.x * MM;
@@ -128,8 +129,25 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         const int64_t row = row_idx ? (int64_t)row_idx[pt] : (per_point ? pt : 0);
         row_off[tid] = row * pl.D;
     }
-    if (tid < SMAX) srow_s[tid] = (tid < pl.S) ? pl.sample_hs_row[tid] : -1;
+    // sample positions: 0..3 = histosys rows (sample hs_row_sample[r]), 4..7 = samples without histosys
+    if (tid < SMAX) {
+        int smp = -1;
+        if (tid < 4) {
+            if (tid < pl.R) smp = pl.hs_row_sample[tid];
+        } else {
+            int cnt = 0;
+            for (int s2 = 0; s2 < pl.S; ++s2)
+                if (pl.sample_hs_row[s2] < 0) {
+                    if (cnt == tid - 4) smp = s2;
+                    ++cnt;
+                }
+        }
+        srow_s[tid] = smp;
+    }
     __syncthreads();
+    int pos_smp[SMAX];
+#pragma unroll
+    for (int q = 0; q < SMAX; ++q) pos_smp[q] = srow_s[q];
     int issued = 0;    // table chunks requested so far (thread 0)
     int consumed = 0;  // table chunks consumed so far (uniform)
     const int per_tile = (GRAD ? 2 : 1) * NCH;
@@ -224,7 +242,12 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 const int ks = i / BT, bl = i - ks * BT;
                 bf_s[i] = pl.bf_par[(int64_t)ks * NB + min(b0 + bl, NB - 1)];
             }
-            if (tid < BT) seg_s[tid] = pl.bin_seg[min(b0 + tid, NB - 1)];
+            if (tid < BT) {
+                seg_s[tid] = pl.bin_seg[min(b0 + tid, NB - 1)];
+                int any = 0;
+                for (int ks = 0; ks < pl.K * S; ++ks) any |= (pl.bf_par[(int64_t)ks * NB + min(b0 + tid, NB - 1)] >= 0);
+                bfany_s[tid] = any;
+            }
             // observed counts of the 32 points: a warp reads one point's 32 bins per pass
             for (int q = warp; q < MM; q += NTHR / 32) {
                 nd_s[q * (BT + 1) + lane] = data[row_off[q] + min(b0 + lane, NB - 1)];
@@ -232,7 +255,81 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         }
         __syncthreads();
 
-        // ---------------------------------------------------------------- epilogue (rolled)
+        // ---------------------------------------------------------------- epilogue
+        // positions 0..3 are the histosys rows (Delta in cell[0..3]), 4..7 the other samples.
+        // Fast path (the warp's 4 bins lie in one segment): the 4 bins are processed as 4
+        // interleaved dependency chains (the log / divide chains are ~1000 cycles each and only
+        // two warps share a scheduler); slow path: one bin at a time with a segment switch.
+        auto switch_segment = [&](int seg) {
+            if (GRAD && gseg >= 0) {
+#pragma unroll
+                for (int q = 0; q < SMAX; ++q)
+                    if (pos_smp[q] >= 0 && gacc[q] != 0.0)
+                        atomicAdd(&w.GsegT[((int64_t)pos_smp[q] * pl.NSEG + gseg) * ld + p], gacc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < SMAX; ++q) {
+                gacc[q] = 0.0;
+                // scalar factors of this point in the new segment stay in registers
+                fseg[q] = (pos_smp[q] >= 0) ? w.FsegT[((int64_t)pos_smp[q] * pl.NSEG + seg) * ld + p] : 0.0;
+            }
+            gseg = seg;
+        };
+        const int seg_first = seg_s[4 * warp], seg_last = seg_s[4 * warp + 3];
+        const bool plain = !HASBF || !(bfany_s[4 * warp] | bfany_s[4 * warp + 1] | bfany_s[4 * warp + 2] |
+                                       bfany_s[4 * warp + 3]);
+        if (seg_first == seg_last && plain) {
+            if (seg_first != gseg) switch_segment(seg_first);
+            double lam[4], wgt[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int bl = 4 * warp + j;
+                const double4 dlt = *reinterpret_cast<const double4*>(wfs + (size_t)lane * CS + 4 * bl);
+                const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < SMAX; ++q) {
+                    if (pos_smp[q] >= 0) {
+                        const int s = pos_smp[q];
+                        double base = nom_s[s * BT + bl];
+                        if (q < 4) base += dl[q];
+                        acc = fma(fseg[q], base, acc);
+                    }
+                }
+                lam[j] = acc;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int bl = 4 * warp + j;
+                const bool valid = tile * BT + bl < NB;
+                const double n = nd_s[lane * (BT + 1) + bl];
+                if (valid) val += hf_pois_term(n, lam[j]);
+                wgt[j] = valid ? (n / lam[j] - 1.0) : 0.0;
+            }
+            if (GRAD) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int bl = 4 * warp + j;
+                    double* cell = wfs + (size_t)lane * CS + 4 * bl;
+                    const double4 dlt = *reinterpret_cast<const double4*>(cell);
+                    const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
+                    double wf[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int q = 0; q < SMAX; ++q) {
+                        if (pos_smp[q] >= 0) {
+                            const int s = pos_smp[q];
+                            double base = nom_s[s * BT + bl];
+                            if (q < 4) base += dl[q];
+                            gacc[q] = fma(wgt[j], base, gacc[q]);
+                            if (q < 4) wf[q] = wgt[j] * fseg[q];
+                        }
+                    }
+                    double4 st;  // A' operand of the backward product
+                    st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
+                    *reinterpret_cast<double4*>(cell) = st;
+                }
+            }
+        } else {
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             const int bl = 4 * warp + j;
@@ -241,61 +338,50 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             const int bb = valid ? b : NB - 1;
             const int seg = seg_s[bl];
             double* cell = wfs + (size_t)lane * CS + 4 * bl;
-            if (seg != gseg) {  // warp-uniform: all lanes look at the same bin
-                if (GRAD && gseg >= 0) {
+            if (seg != gseg) switch_segment(seg);  // warp-uniform: all lanes look at the same bin
+            const double4 dlt = *reinterpret_cast<const double4*>(cell);
+            double basev[SMAX], bfv[SMAX];
+            basev[0] = dlt.x; basev[1] = dlt.y; basev[2] = dlt.z; basev[3] = dlt.w;
 #pragma unroll
-                    for (int s = 0; s < SMAX; ++s)
-                        if (s < S && gacc[s] != 0.0)
-                            atomicAdd(&w.GsegT[((int64_t)s * pl.NSEG + gseg) * ld + p], gacc[s]);
-                }
-#pragma unroll
-                for (int s = 0; s < SMAX; ++s) {
-                    gacc[s] = 0.0;
-                    // scalar factors of this point in the new segment stay in registers
-                    fseg[s] = (s < S) ? w.FsegT[((int64_t)s * pl.NSEG + seg) * ld + p] : 0.0;
-                }
-                gseg = seg;
-            }
+            for (int q = 4; q < SMAX; ++q) basev[q] = 0.0;
             double lam = 0.0;
-            double bfv[SMAX], basev[SMAX];
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) {
-                bfv[s] = 1.0;
-                basev[s] = 0.0;
-                if (s < S) {
-                    for (int k = 0; k < pl.K; ++k) {
-                        const int q = bf_s[(k * S + s) * BT + bl];
-                        if (q >= 0) bfv[s] *= w.parsT[(int64_t)q * ld + p];
+            for (int q = 0; q < SMAX; ++q) {
+                bfv[q] = 1.0;
+                if (pos_smp[q] >= 0) {
+                    const int s = pos_smp[q];
+                    if (HASBF) {
+                        for (int k = 0; k < pl.K; ++k) {
+                            const int par = bf_s[(k * S + s) * BT + bl];
+                            if (par >= 0) bfv[q] *= w.parsT[(int64_t)par * ld + p];
+                        }
                     }
-                    const int row = srow_s[s];
-                    basev[s] = nom_s[s * BT + bl] + (row >= 0 ? cell[row] : 0.0);
-                    double r = fseg[s] * bfv[s] * basev[s];
-                    if (pl.has_clip_sample) r = fmax(r, pl.clip_sample);
-                    lam += r;
+                    basev[q] += nom_s[s * BT + bl];
+                    lam = fma(fseg[q] * bfv[q], basev[q], lam);
                 }
-            }
-            bool live = true;
-            if (pl.has_clip_bin && lam < pl.clip_bin) {
-                lam = pl.clip_bin;
-                live = false;
             }
             const double n = nd_s[lane * (BT + 1) + bl];
             if (valid) val += hf_pois_term(n, lam);
             if (GRAD) {
-                const double wgt = (valid && live) ? (n / lam - 1.0) : 0.0;
+                const double wgt = valid ? (n / lam - 1.0) : 0.0;
+                double wf[4];
 #pragma unroll
-                for (int s = 0; s < SMAX; ++s) {
-                    if (s < S) {
-                        const double r = fseg[s] * bfv[s] * basev[s];
-                        const bool lv = !(pl.has_clip_sample && r < pl.clip_sample);
-                        const double wl = lv ? wgt : 0.0;
-                        gacc[s] += wl * bfv[s] * basev[s];
-                        if (pl.K > 0 && wl != 0.0) cell_bf_grad(pl, w, ld, p, s, bb, wl * fseg[s] * basev[s]);
-                        const int row = srow_s[s];
-                        if (row >= 0) cell[row] = wl * fseg[s] * bfv[s];  // A' of the backward product
+                for (int q = 0; q < SMAX; ++q) {
+                    if (pos_smp[q] >= 0) {
+                        const double wb = wgt * bfv[q];
+                        gacc[q] = fma(wb, basev[q], gacc[q]);
+                        if (q < 4) wf[q] = wb * fseg[q];
+                        if (HASBF && wgt != 0.0)
+                            cell_bf_grad(pl, w, ld, p, pos_smp[q], bb, wgt * fseg[q] * basev[q]);
+                    } else if (q < 4) {
+                        wf[q] = 0.0;
                     }
                 }
+                double4 st;  // A' operand of the backward product
+                st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
+                *reinterpret_cast<double4*>(cell) = st;
             }
+        }
         }
 
         // ---------------------------------------------------------------- backward contraction
@@ -329,9 +415,9 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     if (GRAD) {
         if (gseg >= 0) {
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s)
-                if (s < S && gacc[s] != 0.0)
-                    atomicAdd(&w.GsegT[((int64_t)s * pl.NSEG + gseg) * ld + p], gacc[s]);
+            for (int q = 0; q < SMAX; ++q)
+                if (pos_smp[q] >= 0 && gacc[q] != 0.0)
+                    atomicAdd(&w.GsegT[((int64_t)pos_smp[q] * pl.NSEG + gseg) * ld + p], gacc[q]);
         }
         // bacc[chunk][ni] = C'[point 8*warp+g][k = chunk*KC + 8ni + 2t, +1] = (T1, T2) sums of one modifier
         const int64_t pw = pt0 + 8 * (warp & 3) + g;  // the two cell halves add their partial sums
@@ -374,7 +460,7 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
     const DevPlan& pl = plan->d;
     const int KS = hf_mma_ks(pl.H);
     size_t smem = sizeof(double) * ((size_t)MM * KS + 2 * KC * CS + MM * CS) + 64 + 8 * MM + 128 +
-                  sizeof(double) * (MM * (BT + 1) + SMAX * BT) + sizeof(int) * (BT + SMAX + (size_t)pl.K * pl.S * BT);
+                  sizeof(double) * (MM * (BT + 1) + SMAX * BT) + sizeof(int) * (2 * BT + SMAX + (size_t)pl.K * pl.S * BT);
     const int64_t half = KS / 2;
     hf_prep_mma_kernel<<<(unsigned)((ld * half + 255) / 256), 256, 0, st>>>(pl, plan->w, ld, KS);
     plan->launches++;
@@ -385,15 +471,18 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
         cudaEventCreate(&e1);
         cudaEventRecord(e0, st);
     }
-    if (grad) {
-        auto k = hf_main_mma_kernel<NCH, true>;
-        HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, NTHR, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS);
-    } else {
-        auto k = hf_main_mma_kernel<NCH, false>;
-        HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, NTHR, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS);
+#define HF_MMA_GO(G_, BF_)                                                                          \
+    {                                                                                               \
+        auto k = hf_main_mma_kernel<NCH, G_, BF_>;                                                  \
+        HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k<<<grid, NTHR, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS);              \
     }
+    if (grad) {
+        if (pl.K > 0) HF_MMA_GO(true, true) else HF_MMA_GO(true, false)
+    } else {
+        if (pl.K > 0) HF_MMA_GO(false, true) else HF_MMA_GO(false, false)
+    }
+#undef HF_MMA_GO
     if (plan->timing) {
         cudaEventRecord(e1, st);
         plan->ev.push_back(e0);
