@@ -315,9 +315,15 @@ def run_b200(args):
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     main_avg_ms = main_ms / max(main_n, 1)
     achieved_tf = FLOP_PER_EVAL * B / (main_avg_ms * 1e-3) / 1e12
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["hf_main_mma_kernel_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
-        "bound": "fp64", "kernel": "hf_main_kernel", "achieved": achieved_tf, "peak": fp64_peak,
-        "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": None,
+        "bound": "fp64", "kernel": "hf_main_mma_kernel (DMMA) / hf_main_kernel (DFMA fallback)",
+        "achieved": achieved_tf, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
         "peak_source": "measured live: hf_fp64_peak (16 independent DFMA chains/thread, 148x8 CTAs)",
         "algorithmic_flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": B,
         "kernel_ms_per_launch": main_avg_ms, "kernel_share_of_step": main_ms / ms,
@@ -369,7 +375,7 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
 
 
-def toy_fit_metric(batched, ntoys=20000):
+def toy_fit_metric(batched, ntoys=100000):
     """secondary metric: q~ toy fits/s on C3 (config 3), device-resident toys"""
     import pyhf
     import torch
