@@ -413,6 +413,33 @@ def stage_c4():
     print("wrote", path, os.path.getsize(path))
 
 
+def stage_scan():
+    """config 2: 41-point asymptotic q~ CLs scan + upper limit on the 2-bin x 2-channel model
+    (infer/intervals/upper_limits.py:148-213), default and tight reference optimizer"""
+    import numpy as np
+    key = "2bin_2channel"
+    src, spec, exp = load_validation_fixtures()[key]
+    model = pyhf.Model(spec, modifier_settings={"normsys": {"interpcode": "code1"}}, poi_name="mu")
+    data = source_data(src, model)
+    scan = np.linspace(0, 5, 41)
+    d = {"scan": scan, "data": np.asarray(data, float)}
+    for tag, kw in (("", {}), ("_tight", {"tolerance": 1e-12})):
+        pyhf.set_backend("numpy", pyhf.optimize.scipy_optimizer(**kw))
+        obs, exps, (sc, res) = pyhf.infer.intervals.upper_limits.upper_limit(
+            data, model, scan, return_results=True)
+        d[f"obs_limit{tag}"] = float(obs)
+        d[f"exp_limits{tag}"] = np.array([float(e) for e in exps])
+        d[f"cls_obs{tag}"] = np.array([float(r[0]) for r in res])
+        d[f"cls_exp{tag}"] = np.array([[float(e) for e in r[1]] for r in res])
+    pyhf.set_backend("numpy", "scipy")
+    d["spec_json"] = np.array(json.dumps(spec))
+    d["meta_json"] = np.array(json.dumps(dict(name="scan_2bin_2channel", poi_name="mu",
+                                              settings={"modifier_settings": {"normsys": {"interpcode": "code1"}}})))
+    np.savez_compressed(os.path.join(HERE, "scan_2bin_2channel.npz"), **d)
+    print("obs UL", d["obs_limit"], d["obs_limit_tight"], "exp", d["exp_limits"], d["exp_limits_tight"])
+
+
+
 if __name__ == "__main__":
     stages = sys.argv[1:] or ["small", "toys", "c4", "c3"]
     for st in stages:

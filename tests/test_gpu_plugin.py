@@ -114,3 +114,38 @@ def test_unchanged_toycalculator(b200, golden):
     # asymptotic value 0.0525; 300 toys -> MC error ~0.02
     assert abs(float(cls_obs) - 0.0525) < 0.08
     assert len(cls_exp) == 5
+
+
+def test_config2_asymptotic_scan_upper_limit(b200, golden):
+    """BASELINE config 2: 41-point q~ CLs scan through the UNCHANGED
+    pyhf.infer.intervals.upper_limits.upper_limit (205 fits through b200_optimizer; exercises the
+    DeviceArray negative-step slicing of upper_limits.py:16-18), and the same scan as ONE batched
+    K3 call with per-row fixed POI values"""
+    pyhf = b200
+    g = golden("scan_2bin_2channel")
+    model = g.model()
+    data = g["data"].tolist()
+    scan = g["scan"]
+    obs, exp, (sc, res) = pyhf.infer.intervals.upper_limits.upper_limit(data, model, scan, return_results=True)
+    assert abs(float(obs) - float(g["obs_limit_tight"])) < 1e-6
+    assert np.allclose([float(e) for e in exp], g["exp_limits_tight"], atol=1e-6, rtol=0)
+    assert abs(float(obs) - 1.0299091) < 5e-6  # SURVEY.md Appendix F probe (default-tolerance reference)
+    cls_obs = np.array([float(r[0]) for r in res])
+    assert np.abs(cls_obs - g["cls_obs_tight"]).max() < 1e-6
+    # batched: all 41 fixed-POI fits in one call equal the per-point fits pyhf just made
+    from pyhf_b200 import batched
+
+    plan = batched.plan_for(model)
+    hp = plan.host
+    init = np.tile(hp.init, (len(scan), 1))
+    init[:, hp.poi_index] = scan
+    fixed = hp.fixed.copy()
+    fixed[hp.poi_index] = 1
+    rb = plan.fit(np.asarray(data), init=init, fixed=fixed)
+    free = plan.fit(np.asarray(data))
+    q = np.maximum(rb.fun.cpu().numpy() - float(free.fun[0]), 0.0)
+    q[scan < float(free.x[0, hp.poi_index])] = 0.0
+    for i in (8, 20, 40):
+        qi = float(pyhf.infer.test_statistics.qmu_tilde(scan[i], data, model, model.config.suggested_init(),
+                                                        model.config.suggested_bounds(), model.config.suggested_fixed()))
+        assert abs(qi - q[i]) < 1e-6
