@@ -92,6 +92,7 @@ __device__ __forceinline__ void cell_bf_grad(const DevPlan& pl, const Work& w, i
 }
 
 constexpr int SMAX = 8;  // samples handled by the register-resident per-(sample, segment) sums
+constexpr int NSTAGE = 2;  // table-chunk buffers in flight (42 KB each); 3 measured no faster
 constexpr int NTHR = 256;  // 8 warps: forward = 16 cells each, backward = (8 points) x (64 cells) each
 
 template <int NCH, bool GRAD, bool HASBF>
@@ -100,10 +101,10 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                    int per_point, const int* __restrict__ row_idx, int KS) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* coefs = reinterpret_cast<double*>(smem_raw);            // [MM][KS]
-    double* tbuf = coefs + (size_t)MM * KS;                          // [2][KC*CS]
-    double* wfs = tbuf + 2 * KC * CS;                                // [MM][CS]  Delta, then w*F
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs + MM * CS);     // [3]
-    int64_t* row_off = reinterpret_cast<int64_t*>(bars + 4);         // [MM]
+    double* tbuf = coefs + (size_t)MM * KS;                          // [NSTAGE][KC*CS]
+    double* wfs = tbuf + NSTAGE * KC * CS;                           // [MM][CS]  Delta, then w*F
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs + MM * CS);     // [NSTAGE + 1]
+    int64_t* row_off = reinterpret_cast<int64_t*>(bars + 8);         // [MM]
     double* nd_s = reinterpret_cast<double*>(row_off + MM);          // [MM][BT+1] observed counts
     double* nom_s = nd_s + MM * (BT + 1);                            // [S][BT]    nominal of the tile
     int* seg_s = reinterpret_cast<int*>(nom_s + SMAX * BT);          // [BT]
@@ -117,9 +118,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     const double* tt = pl.mma_tt;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_init(&bars[2], 1);
+        for (int i = 0; i <= NSTAGE; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -155,19 +154,19 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     auto issue_next = [&]() {  // thread 0 only
         if (issued < n_items) {
             const int tile = issued / per_tile, chunk = (issued % per_tile) % NCH;
-            uint64_t* bar = &bars[issued & 1];
+            uint64_t* bar = &bars[issued % NSTAGE];
             mbar_expect_tx(bar, CHUNK_BYTES);
-            bulk_g2s(tbuf + (size_t)(issued & 1) * KC * CS,
+            bulk_g2s(tbuf + (size_t)(issued % NSTAGE) * KC * CS,
                      tt + ((size_t)tile * NCH + chunk) * KC * CS, CHUNK_BYTES, bar);
         }
         ++issued;
     };
     if (tid == 0) {
-        mbar_expect_tx(&bars[2], (uint32_t)(MM * KS * sizeof(double)));
-        bulk_g2s(coefs, w.coefK + pt0 * KS, (uint32_t)(MM * KS * sizeof(double)), &bars[2]);
-        issue_next();
+        mbar_expect_tx(&bars[NSTAGE], (uint32_t)(MM * KS * sizeof(double)));
+        bulk_g2s(coefs, w.coefK + pt0 * KS, (uint32_t)(MM * KS * sizeof(double)), &bars[NSTAGE]);
+        for (int i = 0; i < NSTAGE - 1; ++i) issue_next();  // prologue: NSTAGE-1 chunks in flight
     }
-    mbar_wait(&bars[2], 0);
+    mbar_wait(&bars[NSTAGE], 0);
 
     // backward accumulators: this warp's 8 points x all K columns
     double bacc[NCH][NT_BWD][2];
@@ -198,8 +197,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
 #pragma unroll 1
             for (int chunk = 0; chunk < NCH; ++chunk) {
                 if (tid == 0) issue_next();
-                mbar_wait(&bars[consumed & 1], (consumed >> 1) & 1);
-                const double* tb = tbuf + (size_t)(consumed & 1) * KC * CS + 16 * warp + g;
+                mbar_wait(&bars[consumed % NSTAGE], (consumed / NSTAGE) & 1);
+                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CS + 16 * warp + g;
                 const double* ca = coefs + (size_t)g * KS + chunk * KC + t;
 #pragma unroll 5
                 for (int k4 = 0; k4 < KC / 4; ++k4) {
@@ -278,55 +277,65 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         const int seg_first = seg_s[4 * warp], seg_last = seg_s[4 * warp + 3];
         const bool plain = !HASBF || !(bfany_s[4 * warp] | bfany_s[4 * warp + 1] | bfany_s[4 * warp + 2] |
                                        bfany_s[4 * warp + 3]);
-        if (seg_first == seg_last && plain) {
-            if (seg_first != gseg) switch_segment(seg_first);
-            double lam[4], wgt[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int bl = 4 * warp + j;
-                const double4 dlt = *reinterpret_cast<const double4*>(wfs + (size_t)lane * CS + 4 * bl);
-                const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < SMAX; ++q) {
-                    if (pos_smp[q] >= 0) {
-                        const int s = pos_smp[q];
-                        double base = nom_s[s * BT + bl];
-                        if (q < 4) base += dl[q];
-                        acc = fma(fseg[q], base, acc);
-                    }
-                }
-                lam[j] = acc;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int bl = 4 * warp + j;
-                const bool valid = tile * BT + bl < NB;
-                const double n = nd_s[lane * (BT + 1) + bl];
-                if (valid) val += hf_pois_term(n, lam[j]);
-                wgt[j] = valid ? (n / lam[j] - 1.0) : 0.0;
-            }
-            if (GRAD) {
+        // bins are ordered, so the warp's 4 bins span at most two segments iff the inner ones
+        // belong to the first or the last one; each segment gets one (masked) pass
+        const bool two_seg = (seg_s[4 * warp + 1] == seg_first || seg_s[4 * warp + 1] == seg_last) &&
+                             (seg_s[4 * warp + 2] == seg_first || seg_s[4 * warp + 2] == seg_last);
+        if (plain && two_seg) {
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int seg_cur = pass ? seg_last : seg_first;
+                if (pass && seg_last == seg_first) break;
+                if (seg_cur != gseg) switch_segment(seg_cur);
+                double lam[4], wgt[4];
+                bool act[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int bl = 4 * warp + j;
-                    double* cell = wfs + (size_t)lane * CS + 4 * bl;
-                    const double4 dlt = *reinterpret_cast<const double4*>(cell);
+                    act[j] = seg_s[bl] == seg_cur;
+                    const double4 dlt = *reinterpret_cast<const double4*>(wfs + (size_t)lane * CS + 4 * bl);
                     const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
-                    double wf[4] = {0.0, 0.0, 0.0, 0.0};
+                    double acc = 0.0;
 #pragma unroll
                     for (int q = 0; q < SMAX; ++q) {
                         if (pos_smp[q] >= 0) {
-                            const int s = pos_smp[q];
-                            double base = nom_s[s * BT + bl];
+                            double base = nom_s[pos_smp[q] * BT + bl];
                             if (q < 4) base += dl[q];
-                            gacc[q] = fma(wgt[j], base, gacc[q]);
-                            if (q < 4) wf[q] = wgt[j] * fseg[q];
+                            acc = fma(fseg[q], base, acc);
                         }
                     }
-                    double4 st;  // A' operand of the backward product
-                    st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
-                    *reinterpret_cast<double4*>(cell) = st;
+                    lam[j] = acc;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int bl = 4 * warp + j;
+                    const bool valid = (tile * BT + bl < NB) && act[j];
+                    const double n = nd_s[lane * (BT + 1) + bl];
+                    if (valid) val += hf_pois_term(n, lam[j]);
+                    wgt[j] = valid ? (n / lam[j] - 1.0) : 0.0;
+                }
+                if (GRAD) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (!act[j]) continue;  // warp-uniform
+                        const int bl = 4 * warp + j;
+                        double* cell = wfs + (size_t)lane * CS + 4 * bl;
+                        const double4 dlt = *reinterpret_cast<const double4*>(cell);
+                        const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
+                        double wf[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int q = 0; q < SMAX; ++q) {
+                            if (pos_smp[q] >= 0) {
+                                double base = nom_s[pos_smp[q] * BT + bl];
+                                if (q < 4) base += dl[q];
+                                gacc[q] = fma(wgt[j], base, gacc[q]);
+                                if (q < 4) wf[q] = wgt[j] * fseg[q];
+                            }
+                        }
+                        double4 st;  // A' operand of the backward product
+                        st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
+                        *reinterpret_cast<double4*>(cell) = st;
+                    }
                 }
             }
         } else {
@@ -390,10 +399,10 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
 #pragma unroll
             for (int chunk = 0; chunk < NCH; ++chunk) {
                 if (tid == 0) issue_next();
-                mbar_wait(&bars[consumed & 1], (consumed >> 1) & 1);
+                mbar_wait(&bars[consumed % NSTAGE], (consumed / NSTAGE) & 1);
                 // warp = (m-tile: points 8*(warp&3)+g) x (cell half: 64*(warp>>2) ..)
                 const int c0 = 64 * (warp >> 2);
-                const double* tb = tbuf + (size_t)(consumed & 1) * KC * CS + (size_t)g * CS + t + c0;
+                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CS + (size_t)g * CS + t + c0;
                 const double* arow = wfs + (size_t)(8 * (warp & 3) + g) * CS + t + c0;
 #pragma unroll 4
                 for (int c4 = 0; c4 < NC / 8; ++c4) {
@@ -459,7 +468,7 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
            const int* row_idx, bool grad, cudaStream_t st) {
     const DevPlan& pl = plan->d;
     const int KS = hf_mma_ks(pl.H);
-    size_t smem = sizeof(double) * ((size_t)MM * KS + 2 * KC * CS + MM * CS) + 64 + 8 * MM + 128 +
+    size_t smem = sizeof(double) * ((size_t)MM * KS + NSTAGE * KC * CS + MM * CS) + 64 + 8 * MM + 128 +
                   sizeof(double) * (MM * (BT + 1) + SMAX * BT) + sizeof(int) * (2 * BT + SMAX + (size_t)pl.K * pl.S * BT);
     const int64_t half = KS / 2;
     hf_prep_mma_kernel<<<(unsigned)((ld * half + 255) / 256), 256, 0, st>>>(pl, plan->w, ld, KS);
