@@ -233,6 +233,8 @@ void hf_plan_destroy(hf_plan* plan) {
     cudaFree(plan->fit_block);
     cudaFree(plan->stage_block);
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+    if (plan->s_in) cudaStreamDestroy(plan->s_in);
+    if (plan->s_out) cudaStreamDestroy(plan->s_out);
     delete plan;
 }
 
@@ -373,14 +375,59 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
     double* d_data = d_pars + n_pars;
     double* d_out = d_data + n_data;
     double* d_grad = grad_host ? d_out + B : nullptr;
-    HF_CUDA_OK(cudaMemcpyAsync(d_pars, pars_host, sizeof(double) * n_pars, cudaMemcpyHostToDevice, st));
-    HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * n_data, cudaMemcpyHostToDevice, st));
-    rc = hf_eval_launch(plan, d_pars, d_data, data_rows, B, d_out, d_grad, st);
-    if (rc) return rc;
-    HF_CUDA_OK(cudaMemcpyAsync(out_host, d_out, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    if (grad_host)
-        HF_CUDA_OK(cudaMemcpyAsync(grad_host, d_grad, sizeof(double) * n_pars, cudaMemcpyDeviceToHost, st));
+    // Pipeline over chunks of points: H2D of chunk i+1, the kernels of chunk i and D2H of chunk
+    // i-1 overlap (PCIe is full duplex); the copy streams are ordered against `st` by events.
+    const int64_t CH = 16384;
+    if (B <= 2 * CH || data_rows != 1) {
+        HF_CUDA_OK(cudaMemcpyAsync(d_pars, pars_host, sizeof(double) * n_pars, cudaMemcpyHostToDevice, st));
+        HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * n_data, cudaMemcpyHostToDevice, st));
+        rc = hf_eval_launch(plan, d_pars, d_data, data_rows, B, d_out, d_grad, st);
+        if (rc) return rc;
+        HF_CUDA_OK(cudaMemcpyAsync(out_host, d_out, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+        if (grad_host)
+            HF_CUDA_OK(cudaMemcpyAsync(grad_host, d_grad, sizeof(double) * n_pars, cudaMemcpyDeviceToHost, st));
+        HF_CUDA_OK(cudaStreamSynchronize(st));
+        return HF_OK;
+    }
+    if (!plan->s_in) {
+        HF_CUDA_OK(cudaStreamCreateWithFlags(&plan->s_in, cudaStreamNonBlocking));
+        HF_CUDA_OK(cudaStreamCreateWithFlags(&plan->s_out, cudaStreamNonBlocking));
+    }
+    const int64_t nch = (B + CH - 1) / CH;
+    std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);
+    cudaEvent_t ev_start;
+    HF_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    HF_CUDA_OK(cudaEventRecord(ev_start, st));  // everything queued on `st` before this call is visible
+    HF_CUDA_OK(cudaStreamWaitEvent(plan->s_in, ev_start, 0));
+    HF_CUDA_OK(cudaStreamWaitEvent(plan->s_out, ev_start, 0));
+    HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * n_data, cudaMemcpyHostToDevice, plan->s_in));
+    for (int64_t c = 0; c < nch; ++c) {
+        const int64_t b0 = c * CH, nb = std::min<int64_t>(CH, B - b0);
+        HF_CUDA_OK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        HF_CUDA_OK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        HF_CUDA_OK(cudaMemcpyAsync(d_pars + b0 * P, pars_host + b0 * P, sizeof(double) * nb * P,
+                                   cudaMemcpyHostToDevice, plan->s_in));
+        HF_CUDA_OK(cudaEventRecord(ev_in[c], plan->s_in));
+    }
+    for (int64_t c = 0; c < nch; ++c) {
+        const int64_t b0 = c * CH, nb = std::min<int64_t>(CH, B - b0);
+        HF_CUDA_OK(cudaStreamWaitEvent(st, ev_in[c], 0));
+        rc = hf_eval_launch(plan, d_pars + b0 * P, d_data, 1, nb, d_out + b0, d_grad ? d_grad + b0 * P : nullptr, st);
+        if (rc) return rc;
+        HF_CUDA_OK(cudaEventRecord(ev_done[c], st));
+        HF_CUDA_OK(cudaStreamWaitEvent(plan->s_out, ev_done[c], 0));
+        HF_CUDA_OK(cudaMemcpyAsync(out_host + b0, d_out + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, plan->s_out));
+        if (grad_host)
+            HF_CUDA_OK(cudaMemcpyAsync(grad_host + b0 * P, d_grad + b0 * P, sizeof(double) * nb * P,
+                                       cudaMemcpyDeviceToHost, plan->s_out));
+    }
+    HF_CUDA_OK(cudaStreamSynchronize(plan->s_out));
     HF_CUDA_OK(cudaStreamSynchronize(st));
+    for (int64_t c = 0; c < nch; ++c) {
+        cudaEventDestroy(ev_in[c]);
+        cudaEventDestroy(ev_done[c]);
+    }
+    cudaEventDestroy(ev_start);
     return HF_OK;
 }
 

@@ -210,6 +210,7 @@ struct hf_plan {
     void* stage_block = nullptr;
     size_t stage_bytes = 0;
     int64_t launches = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host-buffer entry points
     bool timing = false;
     std::vector<cudaEvent_t> ev;  // start/stop pairs of hf_main_kernel launches
     int device = 0;
