@@ -70,7 +70,16 @@ def c4_inputs(B, seed=0):
         np.random.seed(0)
         data = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(hp.init)).sample((1,))[0], dtype=np.float64)
     except ImportError:
-        raise SystemExit("bench.py needs the staged reference (baseline/_ref) to build the C4 workspace")
+        # reference not staged on this box: the pyhf-free plan compiler builds the same tables
+        # (tests/test_compile.py); the observed data is then drawn by numpy at the suggested_init expectation
+        from pyhf_b200.compile import compile_spec
+
+        hp = compile_spec(synth.spec_c4(), poi_name="mu")
+        rng = np.random.default_rng(0)
+        data = np.empty(hp.n_data)
+        data[: hp.n_bins] = rng.poisson(hp.nominal.sum(axis=0))  # expectation at suggested_init
+        data[hp.n_bins + hp.g_aux] = rng.normal(hp.auxdata[hp.g_aux], hp.g_sigma)
+        data[hp.n_bins + hp.p_aux] = rng.poisson(hp.p_factor)
     is_alpha = np.zeros(hp.n_pars, bool)
     is_alpha[hp.hs_par] = True
     is_alpha[hp.sf_par[hp.sf_kind != 0]] = True
@@ -377,14 +386,12 @@ def run_b200(args):
 
 def toy_fit_metric(batched, ntoys=100000):
     """secondary metric: q~ toy fits/s on C3 (config 3), device-resident toys"""
-    import pyhf
     import torch
 
     from pyhf_b200 import synth
-    from pyhf_b200.plan import extract_plan
+    from pyhf_b200.compile import compile_spec
 
-    model = pyhf.Model(synth.spec_c3(), poi_name="mu", validate=False)
-    hp = extract_plan(model)
+    hp = compile_spec(synth.spec_c3(), poi_name="mu")  # == extract_plan(pyhf.Model(...)), tests/test_compile.py
     plan = batched.DevicePlan(hp)
     toys = plan.sample_toys(hp.init, ntoys, seed=11)
     batched.qmu_tilde_batch(plan, 1.0, toys[:256])

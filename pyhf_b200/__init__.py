@@ -9,6 +9,7 @@ Hand-written CUDA in ``libhf_b200.so`` (C-ABI: include/hf_b200.h); no CPU fallba
 from .backend import B200Backend, TorchCarrierBackend, b200_backend  # noqa: F401
 from .optimizer import B200Optimizer, b200_optimizer  # noqa: F401
 from .plan import HostPlan, PlanError, extract_plan  # noqa: F401
+from .compile import compile_spec  # noqa: F401
 
 
 def __getattr__(name):

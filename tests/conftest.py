@@ -95,15 +95,23 @@ _synth_cache = {}
 
 
 def synthetic_host_plan(generator):
-    """plan of a synthetic workspace (needs pyhf to build the model)"""
+    """plan of a synthetic workspace: through the live reference model when pyhf is staged, else
+    through the pyhf-free compiler (the two are asserted equal in tests/test_compile.py)"""
     if generator not in _synth_cache:
-        import pyhf
-
         from pyhf_b200 import synth
-        from pyhf_b200.plan import extract_plan
 
-        model = pyhf.Model(getattr(synth, generator)(), poi_name="mu", validate=False)
-        _synth_cache[generator] = (extract_plan(model), model)
+        spec = getattr(synth, generator)()
+        try:
+            import pyhf
+
+            from pyhf_b200.plan import extract_plan
+
+            model = pyhf.Model(spec, poi_name="mu", validate=False)
+            _synth_cache[generator] = (extract_plan(model), model)
+        except ImportError:
+            from pyhf_b200.compile import compile_spec
+
+            _synth_cache[generator] = (compile_spec(spec, poi_name="mu"), None)
     return _synth_cache[generator][0]
 
 

@@ -1,0 +1,59 @@
+"""The pyhf-free plan compiler (pyhf_b200/compile.py) must produce, table for table, what
+``extract_plan`` read off the live reference model when the golden fixtures were made
+(tests/golden/make_golden.py stores those tables as ``plan__*``)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+from pyhf_b200.compile import compile_spec
+from pyhf_b200.plan import PlanError
+
+WITH_PLAN = [n for n in golden_names() if n != "c4"]
+
+
+def _settings(g):
+    s = g.meta.get("settings") or {}
+    return s.get("modifier_settings", s if "normsys" in s or "histosys" in s else None)
+
+
+def _assert_same(a, b):
+    assert set(a) == set(b)
+    for k in sorted(a):
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        assert x.shape == y.shape, (k, x.shape, y.shape)
+        if x.dtype.kind == "f":
+            # code4 coefficients come from a 6x6 matrix product in the reference: same formula,
+            # summation order may differ in the last bits
+            np.testing.assert_allclose(x, y, rtol=1e-13, atol=1e-15, err_msg=k)
+        else:
+            np.testing.assert_array_equal(x, y, err_msg=k)
+
+
+@pytest.mark.parametrize("name", WITH_PLAN)
+def test_compiler_matches_golden_plan(golden, name):
+    g = golden(name)
+    plan = compile_spec(g.spec(), poi_name=g.meta.get("poi_name", "mu"), modifier_settings=_settings(g))
+    _assert_same(plan.arrays(), g.plan_arrays())
+
+
+@pytest.mark.needs_pyhf
+@pytest.mark.parametrize("gen", ["spec_c3", "spec_c4", "spec_hello"])
+def test_compiler_matches_live_extraction(gen):
+    import pyhf
+
+    from pyhf_b200 import synth
+    from pyhf_b200.plan import extract_plan
+
+    spec = getattr(synth, gen)()
+    ref = extract_plan(pyhf.Model(spec, poi_name="mu", validate=False))
+    _assert_same(compile_spec(spec, poi_name="mu").arrays(), ref.arrays())
+
+
+def test_compiler_rejects_out_of_scope():
+    spec = {"channels": [{"name": "c", "samples": [
+        {"name": "s", "data": [1.0], "modifiers": [{"name": "mu", "type": "normfactor", "data": None}]}]}]}
+    with pytest.raises(PlanError):
+        compile_spec(spec, modifier_settings={"normsys": {"interpcode": "code2"}})
+    spec["channels"][0]["samples"][0]["modifiers"].append({"name": "x", "type": "custom", "data": None})
+    with pytest.raises(PlanError):
+        compile_spec(spec)
