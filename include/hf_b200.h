@@ -149,6 +149,16 @@ int hf_fit_batch(hf_plan* plan, const double* data, int64_t data_rows, const dou
                  int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
                  int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
                  int32_t* niter, void* stream);
+/* One lock-step batch over fits that differ in their fixed mask and share data rows: fit i uses
+ * data row data_map[i] (any value in [0, data_rows); NULL = row i, or row 0 when data_rows == 1)
+ * and the mask fixed_alt when use_alt[i] != 0, else fixed (both NULL = hf_fit_batch).  This is how
+ * the constrained (POI fixed, infer/mle.py:138-205) and unconstrained fits of every toy of BOTH
+ * hypotheses (infer/calculators.py:838-869) run as one batch: the slowest fit is waited for once. */
+int hf_fit_batch_mixed(hf_plan* plan, const double* data, int64_t data_rows, const int32_t* data_map,
+                       const double* init, int64_t init_rows, const double* lo, const double* hi,
+                       const uint8_t* fixed, const uint8_t* fixed_alt, const uint8_t* use_alt,
+                       int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
+                       int32_t* niter, void* stream);
 int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,
                       const double* init_host, int64_t init_rows, const double* lo_host,
                       const double* hi_host, const uint8_t* fixed_host, int64_t N,

@@ -67,7 +67,8 @@ def solve_reduced(Hm, g, act, damp=None):
 
 
 def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_step=1e-7,
-              refresh_ratio=0.05, exact_below=10.0, verbose=False):
+              refresh_ratio=0.05, exact_below=10.0, verbose=False, rho_damping=False, damp0=0.0,
+              damp0_edm=np.inf, rho_hi=np.inf, rho_hi_fac=0.2):
     data = np.atleast_2d(data)
     init = np.atleast_2d(init)
     N = max(data.shape[0], init.shape[0])
@@ -106,6 +107,13 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
             xr, gr = x[rows], g[rows]
             act = fixed[None, :] | ((xr <= lo) & (gr > 0)) | ((xr >= hi) & (gr < 0))
             dd, edm = solve_reduced(Hm[rows], gr, act, damp[rows])
+            if it == 0 and damp0 > 0.0:
+                # start-up: a huge predicted decrease means the start point is far outside the
+                # quadratic regime; begin with a damped step instead of discovering it by rejections
+                far = edm > damp0_edm
+                if np.any(far):
+                    damp[rows[far]] = damp0
+                    dd[far], edm[far] = solve_reduced(Hm[rows[far]], gr[far], act[far], damp[rows[far]])
             # curvature refresh: first own Hessian after the start-up step, later when the
             # predicted decrease did not shrink by 1/refresh_ratio
             slow = edm > refresh_ratio * edm_prev[rows]
@@ -153,12 +161,21 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
         slack = 4e-15 * np.maximum(1.0, np.abs(f[live]))
         ok = np.isfinite(ft) & (ft <= f[live] + 1e-4 * dec + slack)
         acc = live[ok]
+        f_old = f[live].copy()
         x[acc], f[acc], g[acc] = xt[ok], ft[ok], gt[ok]
         need_dir[acc] = True
         fresh[acc] = True
         niter[acc] += 1
         nrej[acc] = 0
-        damp[acc] = np.where(0.2 * damp[acc] < 1e-6, 0.0, 0.2 * damp[acc])
+        if rho_damping:
+            # trust-region style: compare the achieved decrease with the one the quadratic model
+            # predicted (>= -dec/2 for a damped Newton step) and move the damping accordingly
+            rho = (f_old[ok] - ft[ok]) / np.maximum(-0.5 * dec[ok], 1e-300)
+            fac = np.where(rho > rho_hi, rho_hi_fac, np.where(rho > 0.75, 0.2, np.where(rho > 0.25, 1.0, 4.0)))
+            nd = np.where((fac > 1.0) & (damp[acc] < 1e-3), 1e-2, fac * damp[acc])
+            damp[acc] = np.where(nd < 1e-6, 0.0, nd)
+        else:
+            damp[acc] = np.where(0.2 * damp[acc] < 1e-6, 0.0, 0.2 * damp[acc])
         rej = live[~ok]
         # rejected: converged if the predicted decrease is below the rounding floor of f,
         # otherwise raise the damping and recompute the direction at the same point

@@ -58,6 +58,8 @@ SIGNATURES = {
     "hf_fit_default_opts": (None, [C.POINTER(FitOpts)]),
     "hf_fit_batch": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64,
                                C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
+    "hf_fit_batch_mixed": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
+                                     C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
     "hf_fit_batch_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64,
                                     C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
     "hf_sample_toys": (C.c_int, [_vp, _vp, _u64, _u64, _i64, _vp, _vp]),

@@ -150,9 +150,13 @@ class DevicePlan:
 
     # ------------------------------------------------------------------ fits
     def fit(self, data, init=None, lo=None, hi=None, fixed=None, max_iter=None, tol_edm=None,
-            tol_step=None, verbose=0):
+            tol_step=None, verbose=0, fixed_alt=None, use_alt=None, data_map=None):
         """K3: N independent bounded fits of 2*NLL.  data [N, D] or [D]; init [N, P] or [P]
-        (fixed parameters keep their init value)."""
+        (fixed parameters keep their init value).
+
+        Mixed batches (hf_fit_batch_mixed): ``data_map`` [N] int32 picks the data row of each fit
+        (data may then have any number of rows); fits with ``use_alt`` [N] != 0 use the mask
+        ``fixed_alt`` [P] instead of ``fixed``."""
         dev = self.device
         data = _dev_tensor(data, dev)
         if data.dim() == 1:
@@ -163,10 +167,21 @@ class DevicePlan:
         lo = self.lo if lo is None else _dev_tensor(lo, dev)
         hi = self.hi if hi is None else _dev_tensor(hi, dev)
         fixed = self.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
-        N = max(data.shape[0], init.shape[0])
+        if data_map is not None:
+            data_map = _dev_tensor(data_map, dev, torch.int32)
+            N = data_map.numel()
+        else:
+            N = max(data.shape[0], init.shape[0])
+        if (fixed_alt is None) != (use_alt is None):
+            raise ValueError("fixed_alt and use_alt go together")
+        if fixed_alt is not None:
+            fixed_alt = _dev_tensor(fixed_alt, dev, torch.uint8)
+            use_alt = _dev_tensor(use_alt, dev, torch.uint8)
+            if use_alt.numel() != N or fixed_alt.numel() != self.P:
+                raise ValueError("bad fixed_alt / use_alt shape")
         if data.shape[1] != self.D or init.shape[1] != self.P:
             raise ValueError("bad data / init shape")
-        if data.shape[0] not in (1, N) or init.shape[0] not in (1, N):
+        if (data_map is None and data.shape[0] not in (1, N)) or init.shape[0] not in (1, N):
             raise ValueError("data and init must have 1 or N rows")
         opts = _lib.FitOpts()
         self._lib.hf_fit_default_opts(C.byref(opts))
@@ -182,10 +197,12 @@ class DevicePlan:
         status = torch.empty(N, dtype=torch.int32, device=dev)
         niter = torch.empty(N, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(self._lib.hf_fit_batch(
-                self._h, _ptr(data), data.shape[0], _ptr(init), init.shape[0], _ptr(lo), _ptr(hi),
-                _ptr(fixed), N, C.byref(opts), _ptr(x), _ptr(fun), _ptr(status), _ptr(niter),
-                _stream()))
+            _lib.check(self._lib.hf_fit_batch_mixed(
+                self._h, _ptr(data), data.shape[0], None if data_map is None else _ptr(data_map),
+                _ptr(init), init.shape[0], _ptr(lo), _ptr(hi), _ptr(fixed),
+                None if fixed_alt is None else _ptr(fixed_alt),
+                None if use_alt is None else _ptr(use_alt), N, C.byref(opts), _ptr(x), _ptr(fun),
+                _ptr(status), _ptr(niter), _stream()))
         return FitResult(x, fun, status, niter)
 
     # ------------------------------------------------------------------ toys
@@ -283,31 +300,52 @@ def pvalue_counts(samples, values):
     return counts
 
 
+def _view(r: "FitResult", sl) -> "FitResult":
+    return FitResult(r.x[sl], r.fun[sl], r.status[sl], r.niter[sl])
+
+
 def qmu_tilde_batch(plan: DevicePlan, mu, data, init=None, lo=None, hi=None, fixed=None,
                     mode="qtilde", warm_start=False, **fit_kw):
     """Test statistic of every row of ``data``: one fixed-POI fit and one free fit per row
-    (reference _tmu_like, infer/test_statistics.py:38-60).  Returns a dict of device tensors."""
+    (reference _tmu_like, infer/test_statistics.py:38-60).  Both fits of all rows run as ONE
+    lock-step batch (hf_fit_batch_mixed) unless ``warm_start`` asks for the free fit to start from
+    the constrained one.  Returns a dict of device tensors."""
     poi = plan.host.poi_index
     if poi < 0:
         raise ValueError("the model has no POI")
     dev = plan.device
     init = plan.init if init is None else _dev_tensor(init, dev)
     fixed = plan.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
+    data = _dev_tensor(data, dev)
+    if data.dim() == 1:
+        data = data.reshape(1, -1)
+    n = data.shape[0]
     init_fixed = init.clone()
     init_fixed[..., poi] = float(mu) if mode != "q0" else 0.0
     fixed_poi = fixed.clone()
     fixed_poi[poi] = 1
-    rf = plan.fit(data, init_fixed, lo, hi, fixed_poi, **fit_kw)
-    ru = plan.fit(data, rf.x if warm_start else init, lo, hi, fixed, **fit_kw)
+    if warm_start:
+        rf = plan.fit(data, init_fixed, lo, hi, fixed_poi, **fit_kw)
+        ru = plan.fit(data, rf.x, lo, hi, fixed, **fit_kw)
+    else:
+        rows = torch.arange(n, dtype=torch.int32, device=dev).repeat(2)
+        use_alt = torch.zeros(2 * n, dtype=torch.uint8, device=dev)
+        use_alt[:n] = 1
+        i_f = init_fixed.reshape(-1, plan.P).expand(n, -1) if init_fixed.dim() == 1 or init_fixed.shape[0] == 1 else init_fixed
+        i_u = init.reshape(-1, plan.P).expand(n, -1) if init.dim() == 1 or init.shape[0] == 1 else init
+        both = plan.fit(data, torch.cat([i_f, i_u]), lo, hi, fixed, fixed_alt=fixed_poi, use_alt=use_alt,
+                        data_map=rows, **fit_kw)
+        rf, ru = _view(both, slice(0, n)), _view(both, slice(n, 2 * n))
     muhat = ru.x[:, poi].contiguous()
-    q = teststat(rf.fun, ru.fun, muhat, float(mu), mode)
+    q = teststat(rf.fun.contiguous(), ru.fun.contiguous(), muhat, float(mu), mode)
     return dict(q=q, muhat=muhat, fixed=rf, free=ru)
 
 
 def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=0, init=None,
                  lo=None, hi=None, fixed=None, mode="qtilde", gather=None, **fit_kw):
     """Toy-based CLs for one signal strength: the arithmetic of ToyCalculator.distributions /
-    pvalues (reference infer/calculators.py:754-915) with every fit batched on the device.
+    pvalues (reference infer/calculators.py:754-915) with every fit batched on the device: the
+    4 * ntoys toy fits (2 hypotheses x {POI fixed, free}) are one lock-step batch.
 
     ``gather`` (optional) maps a per-rank [n] tensor to the all-rank tensor (see dist.py); toys
     [toy_offset, toy_offset + ntoys) are this rank's shard."""
@@ -316,30 +354,38 @@ def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=
     init = plan.init if init is None else _dev_tensor(init, dev)
     fixed = plan.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
     poi = plan.host.poi_index
-    obs = qmu_tilde_batch(plan, mu_test, data_obs, init, lo, hi, fixed, mode, **fit_kw)
-    # generation points: conditional fits at mu_test and at the background-only value
-    bkg_mu = 1.0 if mode == "q0" else 0.0           # calculators.py:808-817
+    # observed test statistic and the generation points (conditional fits at mu_test and at the
+    # background-only value, calculators.py:808-817): 4 fits on the observed data, one batch
+    bkg_mu = 1.0 if mode == "q0" else 0.0
     fp = fixed.clone()
     fp[poi] = 1
+    i_f = init.clone(); i_f[poi] = float(mu_test) if mode != "q0" else 0.0
     i_s = init.clone(); i_s[poi] = float(mu_test)
     i_b = init.clone(); i_b[poi] = bkg_mu
-    gen = plan.fit(data_obs, torch.stack([i_s, i_b]), lo, hi, fp, **fit_kw)
-    sig_toys = plan.sample_toys(gen.x[0], ntoys, seed=seed, offset=toy_offset)
-    bkg_toys = plan.sample_toys(gen.x[1], ntoys, seed=seed + 1, offset=toy_offset)
-    qs = qmu_tilde_batch(plan, mu_test, sig_toys, init, lo, hi, fixed, mode, **fit_kw)
-    qb = qmu_tilde_batch(plan, mu_test, bkg_toys, init, lo, hi, fixed, mode, **fit_kw)
-    q_sig, q_bkg = qs["q"], qb["q"]
+    four = plan.fit(data_obs, torch.stack([i_f, init, i_s, i_b]), lo, hi, fixed, fixed_alt=fp,
+                    use_alt=torch.tensor([1, 0, 1, 1], dtype=torch.uint8, device=dev),
+                    data_map=torch.zeros(4, dtype=torch.int32, device=dev), **fit_kw)
+    obs_f, obs_u, gen = _view(four, slice(0, 1)), _view(four, slice(1, 2)), _view(four, slice(2, 4))
+    muhat_obs = obs_u.x[:, poi].contiguous()
+    qobs = teststat(obs_f.fun.contiguous(), obs_u.fun.contiguous(), muhat_obs, float(mu_test), mode)
+    obs = dict(q=qobs, muhat=muhat_obs, fixed=obs_f, free=obs_u)
+    toys = torch.empty(2 * ntoys, plan.D, dtype=F64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(plan._lib.hf_sample_toys(plan._h, _ptr(gen.x[0].contiguous()), int(seed), int(toy_offset),
+                                            int(ntoys), _ptr(toys[:ntoys]), _stream()))
+        _lib.check(plan._lib.hf_sample_toys(plan._h, _ptr(gen.x[1].contiguous()), int(seed) + 1, int(toy_offset),
+                                            int(ntoys), _ptr(toys[ntoys:]), _stream()))
+    qq = qmu_tilde_batch(plan, mu_test, toys, init, lo, hi, fixed, mode, **fit_kw)
+    q_sig, q_bkg = qq["q"][:ntoys].contiguous(), qq["q"][ntoys:].contiguous()
     if gather is not None:
         q_sig, q_bkg = gather(q_sig), gather(q_bkg)
-    qobs = obs["q"]
     n_sb = pvalue_counts(q_sig, qobs)[0].item()
     n_b = pvalue_counts(q_bkg, qobs)[0].item()
     clsb = n_sb / q_sig.numel()
     clb = n_b / q_bkg.numel()
     return dict(qobs=float(qobs[0]), CLsb=clsb, CLb=clb, CLs=(clsb / clb if clb > 0 else float("nan")),
                 q_sig=q_sig, q_bkg=q_bkg, obs=obs, gen=gen,
-                n_failed=int((qs["fixed"].status != 0).sum() + (qs["free"].status != 0).sum()
-                             + (qb["fixed"].status != 0).sum() + (qb["free"].status != 0).sum()))
+                n_failed=int((qq["fixed"].status != 0).sum() + (qq["free"].status != 0).sum()))
 
 
 def fp64_peak_tflops():

@@ -22,7 +22,8 @@ int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out
 int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const double* init,
                   int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
                   int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
-                  int32_t* niter, cudaStream_t st);
+                  int32_t* niter, cudaStream_t st, const uint8_t* fixed_alt = nullptr,
+                  const uint8_t* use_alt = nullptr, const int32_t* data_map = nullptr);
 int hf_sample_toys_launch(hf_plan* plan, const double* pars, uint64_t seed, uint64_t offset,
                           int64_t N, double* out, cudaStream_t st);
 
@@ -451,6 +452,19 @@ int hf_fit_batch(hf_plan* plan, const double* data, int64_t data_rows, const dou
     }
     return hf_fit_launch(plan, data, data_rows, init, init_rows, lo, hi, fixed, N, opts, x, fun,
                          status, niter, (cudaStream_t)stream);
+}
+
+int hf_fit_batch_mixed(hf_plan* plan, const double* data, int64_t data_rows, const int32_t* data_map,
+                       const double* init, int64_t init_rows, const double* lo, const double* hi,
+                       const uint8_t* fixed, const uint8_t* fixed_alt, const uint8_t* use_alt,
+                       int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
+                       int32_t* niter, void* stream) {
+    if (!plan || !data || !init || !lo || !hi || !fixed || !x || !fun || !status) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    return hf_fit_launch(plan, data, data_rows, init, init_rows, lo, hi, fixed, N, opts, x, fun,
+                         status, niter, (cudaStream_t)stream, fixed_alt, use_alt, data_map);
 }
 
 int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,

@@ -49,14 +49,29 @@ struct FitDev {
     const int* partner;  // [P][ncolors]
     const int* pcol;     // [P]      FD column index of a global free parameter, else -1
     const double *lo, *hi;
-    const uint8_t* fixed;
+    const uint8_t* fixed;         // [P] mask of the batch
+    const uint8_t* fixed_alt;     // [P] second mask (fits with use_alt set), or null
+    const uint8_t* use_alt;       // [N] per fit (global fit index), or null
+    const uint8_t* fixed_struct;  // [P] fixed under every mask of the batch (no FD column)
+    const int* data_map;          // [N] data row of each fit (global fit index), or null
+    int64_t toy0, data_rows;      // first fit of the current chunk; rows of the data array
     double* chol_scratch;  // global-memory factor storage for n > smem capacity
     int chol_in_smem;
     double tol_edm, tol_step, refresh_ratio, exact_below;
     int max_iter;
+    int trace;  // verbose >= 3: print the state of the last few live fits every round
 };
 
 __device__ __forceinline__ double fd_step(double x) { return kFdStep * fmax(1.0, fabs(x)); }
+
+// mask / data row of chunk-local fit `toy`
+__device__ __forceinline__ const uint8_t* fit_mask(const FitDev& s, int64_t toy) {
+    return (s.use_alt && s.use_alt[s.toy0 + toy]) ? s.fixed_alt : s.fixed;
+}
+__device__ __forceinline__ int64_t fit_data_row(const FitDev& s, int64_t toy) {
+    if (s.data_map) return (int64_t)s.data_map[s.toy0 + toy];
+    return (s.data_rows == 1) ? 0 : s.toy0 + toy;
+}
 
 // ---------------------------------------------------------------- state initialisation
 __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64_t init_rows) {
@@ -65,7 +80,7 @@ __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64
     const int64_t i = idx / s.P;
     const int p = (int)(idx - i * s.P);
     double v = init[(init_rows == 1 ? 0 : i) * s.P + p];
-    if (!s.fixed[p]) v = fmin(fmax(v, s.lo[p]), s.hi[p]);
+    if (!fit_mask(s, i)[p]) v = fmin(fmax(v, s.lo[p]), s.hi[p]);
     s.X[idx] = v;
     s.XT[idx] = v;
     if (p == 0) {
@@ -113,7 +128,7 @@ __global__ void fit_fd_points_kernel(FitDev s, const int* __restrict__ list, int
 // data row per refresh entry: Asimov (Fisher mode) or the fit's own data (exact mode)
 __global__ void fit_fd_rows_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
                                    const int* __restrict__ mode, const double* __restrict__ data,
-                                   int64_t data_rows, int64_t toy0, const double* __restrict__ asimov,
+                                   const double* __restrict__ asimov,
                                    double* __restrict__ DR) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nlist * s.D) return;
@@ -121,7 +136,7 @@ __global__ void fit_fd_rows_kernel(FitDev s, const int* __restrict__ list, int64
     const int j = (int)(idx - r * s.D);
     const int64_t toy = list[r];
     const int m = mode ? mode[toy] : 1;
-    DR[idx] = (m == 1) ? asimov[idx] : data[(data_rows == 1 ? 0 : toy0 + toy) * s.D + j];
+    DR[idx] = (m == 1) ? asimov[idx] : data[fit_data_row(s, toy) * s.D + j];
 }
 
 __global__ void fit_gather_x_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
@@ -158,7 +173,7 @@ __global__ void fit_fd_assemble_kernel(FitDev s, const int* __restrict__ list, i
     const int i = (int)(e / s.P), j = (int)(e - (int64_t)i * s.P);
     const int64_t toy = list[r];
     double v;
-    if (s.fixed[i] || s.fixed[j]) {
+    if (s.fixed_struct[i] || s.fixed_struct[j]) {
         v = (i == j) ? 1.0 : 0.0;
     } else {
         const double* gp = GP + r * (int64_t)(s.ncol + 1) * s.P;
@@ -245,9 +260,10 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     // shared memory (P is small).
     __shared__ int s_nloc;
     int* flag = reinterpret_cast<int*>(bvec);  // reuse: bvec is filled after the compaction
+    const uint8_t* mask = fit_mask(s, toy);
     for (int p = tid; p < P; p += nth) {
         const double xv = x[p], gv = g[p];
-        const bool act = s.fixed[p] || (xv <= s.lo[p] && gv > 0.0) || (xv >= s.hi[p] && gv < 0.0);
+        const bool act = mask[p] || (xv <= s.lo[p] && gv > 0.0) || (xv >= s.hi[p] && gv < 0.0);
         flag[p] = act ? 0 : ((s.use_local && s.islocal[p]) ? 1 : 2);
     }
     __syncthreads();
@@ -384,6 +400,232 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     }
 }
 
+// ---------------------------------------------------------------- Newton direction, Schur form
+// Same contract as fit_direction_kernel, for models whose local (per-bin) parameters never share a
+// bin (use_local): the local block of the Hessian is diagonal, so the system is reduced to the
+// global parameters,
+//     S = H_gg + tau I - H_gl (H_ll + tau I)^-1 H_lg ,   S d_g = -g_g + H_gl (H_ll + tau I)^-1 g_l ,
+//     d_l = -(H_ll + tau I)^-1 (g_l + H_lg d_g) ,
+// and only S (n_glob x n_glob, packed) ever lives in shared memory: ~2 KB for C3 (20 globals),
+// 160 KB for C4 (200).  H_gl is streamed through a [ltile][n_glob] staging tile.
+__device__ __forceinline__ void tri_decode(int e, int& a, int& b) {
+    a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while (a * (a + 1) / 2 > e) --a;
+    while ((a + 1) * (a + 2) / 2 <= e) ++a;
+    b = e - a * (a + 1) / 2;
+}
+
+__global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
+                                           int allow_refresh, int ngmax, int nlmax, int ltile) {
+    extern __shared__ __align__(16) double sm[];
+    const int P = s.P;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+    const int64_t toy = (int64_t)list[blockIdx.x];
+    if (toy >= s.NC) return;
+    if (s.done[toy] || !s.need_dir[toy]) return;
+
+    const int ngp = ngmax | 1;
+    double* S = sm;                                  // packed lower triangle of the reduced matrix
+    double* r = S + ngmax * (ngmax + 1) / 2;         // rhs of the global block, then its solution
+    double* z = r + ngmax;
+    double* linv = z + ngmax;                        // 1 / L_kk
+    double* dinv = linv + ngmax;                     // 1 / (H_ll + tau)
+    double* gl = dinv + nlmax;                       // g_l / (H_ll + tau), then d_l
+    double* W = gl + nlmax;                          // [ltile][ngp] staged H_gl
+    int* glb = reinterpret_cast<int*>(W + (size_t)ltile * ngp);
+    int* loc = glb + ngmax;
+    __shared__ int s_ng, s_nl, s_bad;
+    __shared__ double s_red[32], s_red2[32];
+
+    const double* x = s.X + toy * P;
+    const double* g = s.G + toy * P;
+    const double* Hsrc = s.own[toy] ? (s.H + toy * (int64_t)P * P) : s.Hshared;
+
+    // active set (box bounds, fixed parameters), compacted by one warp with ballots
+    const uint8_t* mask = fit_mask(s, toy);
+    if (tid < 32) {
+        int nl_ = 0, ng_ = 0;
+        for (int p0 = 0; p0 < P; p0 += 32) {
+            const int p = p0 + lane;
+            int f = 0;
+            if (p < P) {
+                const double xv = x[p], gv = g[p];
+                const bool act = mask[p] || (xv <= s.lo[p] && gv > 0.0) || (xv >= s.hi[p] && gv < 0.0);
+                f = act ? 0 : (s.islocal[p] ? 1 : 2);
+            }
+            const unsigned ml = __ballot_sync(0xffffffffu, f == 1), mg = __ballot_sync(0xffffffffu, f == 2);
+            const unsigned lt = (1u << lane) - 1u;
+            if (f == 1) loc[nl_ + __popc(ml & lt)] = p;
+            if (f == 2) glb[ng_ + __popc(mg & lt)] = p;
+            nl_ += __popc(ml);
+            ng_ += __popc(mg);
+        }
+        if (lane == 0) { s_nl = nl_; s_ng = ng_; s_bad = 0; }
+    }
+    __syncthreads();
+    const int ng = s_ng, nl = s_nl, npk = ng * (ng + 1) / 2;
+    const int TW = (nth >= 256) ? 16 : 8, TH = nth / TW;
+    const int tx = tid % TW, ty = tid / TW;
+
+    double tau = s.damp[toy];  // Levenberg-Marquardt damping carried by the fit (0 = pure Newton)
+    double maxdiag = -1.0;
+    bool ok = false;
+    for (int attempt = 0; attempt < 40 && !ok; ++attempt) {
+        for (int i = tid; i < nl; i += nth) {
+            const int l = loc[i];
+            const double h = Hsrc[(int64_t)l * P + l] + tau;
+            if (!(h > 0.0) || !isfinite(h)) s_bad = 1;
+            const double di = 1.0 / h;
+            dinv[i] = di;
+            gl[i] = g[l] * di;
+        }
+        for (int e = tid; e < npk; e += nth) {
+            int a, b;
+            tri_decode(e, a, b);
+            S[e] = Hsrc[(int64_t)glb[a] * P + glb[b]] + ((a == b) ? tau : 0.0);
+        }
+        for (int a = tid; a < ng; a += nth) r[a] = -g[glb[a]];
+        __syncthreads();
+        bool bad = s_bad != 0;
+        for (int l0 = 0; l0 < nl && !bad; l0 += ltile) {
+            const int nt = min(ltile, nl - l0);
+            for (int e = tid; e < ng * nt; e += nth) {
+                const int a = e / nt, t = e - a * nt;
+                W[t * ngp + a] = Hsrc[(int64_t)glb[a] * P + loc[l0 + t]];
+            }
+            __syncthreads();
+            for (int e = tid; e < npk; e += nth) {
+                int a, b;
+                tri_decode(e, a, b);
+                double acc = 0.0;
+                for (int t = 0; t < nt; ++t) acc = fma(W[t * ngp + a] * dinv[l0 + t], W[t * ngp + b], acc);
+                S[e] -= acc;
+            }
+            for (int a = tid; a < ng; a += nth) {
+                double acc = 0.0;
+                for (int t = 0; t < nt; ++t) acc = fma(W[t * ngp + a], gl[l0 + t], acc);
+                r[a] += acc;
+            }
+            __syncthreads();
+        }
+        // right-looking Cholesky of S; the diagonal keeps the pivots, linv holds 1/L_kk
+        for (int j = 0; j < ng && !bad; ++j) {
+            const double piv = S[tri(j, j)];
+            if (!(piv > 0.0) || !isfinite(piv)) { bad = true; break; }
+            const double inv = 1.0 / sqrt(piv);
+            for (int i = j + 1 + tid; i < ng; i += nth) S[tri(i, j)] *= inv;
+            if (tid == 0) linv[j] = inv;
+            __syncthreads();
+            for (int i = j + 1 + ty; i < ng; i += TH) {
+                const double lij = S[tri(i, j)];
+                for (int k = j + 1 + tx; k <= i; k += TW) S[tri(i, k)] = fma(-lij, S[tri(k, j)], S[tri(i, k)]);
+            }
+            __syncthreads();
+        }
+        ok = !bad;
+        if (!ok) {
+            if (maxdiag < 0.0) {
+                double m = 0.0;
+                for (int i = tid; i < nl; i += nth) m = fmax(m, fabs(Hsrc[(int64_t)loc[i] * P + loc[i]]));
+                for (int a = tid; a < ng; a += nth) m = fmax(m, fabs(Hsrc[(int64_t)glb[a] * P + glb[a]]));
+                for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) s_red[tid >> 5] = m;
+                __syncthreads();
+                m = 0.0;
+                for (int k = 0; k < (nth + 31) / 32; ++k) m = fmax(m, s_red[k]);
+                maxdiag = m;
+            }
+            __syncthreads();
+            if (tid == 0) s_bad = 0;
+            tau = (tau < 1e-8 * maxdiag) ? 1e-8 * fmax(maxdiag, 1e-300) : tau * 10.0;
+            __syncthreads();
+        }
+    }
+    if (!ok) {
+        if (tid == 0) { s.done[toy] = 1; s.status[toy] = 2; }
+        return;
+    }
+    // L z = r
+    for (int k = 0; k < ng; ++k) {
+        const double zk = r[k] * linv[k];
+        for (int i = k + 1 + tid; i < ng; i += nth) r[i] = fma(-S[tri(i, k)], zk, r[i]);
+        if (tid == 0) z[k] = zk;
+        __syncthreads();
+    }
+    // L^T d_g = z   (d_g is left in r)
+    for (int k = ng - 1; k >= 0; --k) {
+        const double dk = z[k] * linv[k];
+        for (int i = tid; i < k; i += nth) z[i] = fma(-S[tri(k, i)], dk, z[i]);
+        if (tid == 0) r[k] = dk;
+        __syncthreads();
+    }
+    // d_l = -(g_l + H_lg d_g) / (H_ll + tau)   (left in gl)
+    for (int i = tid; i < nl; i += nth) {
+        const int l = loc[i];
+        double acc = 0.0;
+        for (int a = 0; a < ng; ++a) acc = fma(Hsrc[(int64_t)glb[a] * P + l], r[a], acc);
+        gl[i] = -gl[i] - dinv[i] * acc;
+    }
+    __syncthreads();
+    // edm = -g_F . d_F ; step = max |d|
+    double edm = 0.0, step = 0.0;
+    for (int i = tid; i < nl; i += nth) {
+        edm = fma(-g[loc[i]], gl[i], edm);
+        step = fmax(step, fabs(gl[i]));
+    }
+    for (int a = tid; a < ng; a += nth) {
+        edm = fma(-g[glb[a]], r[a], edm);
+        step = fmax(step, fabs(r[a]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        edm += __shfl_xor_sync(0xffffffffu, edm, o);
+        step = fmax(step, __shfl_xor_sync(0xffffffffu, step, o));
+    }
+    if (lane == 0) { s_red[tid >> 5] = edm; s_red2[tid >> 5] = step; }
+    __syncthreads();
+    edm = 0.0; step = 0.0;
+    for (int k = 0; k < (nth + 31) / 32; ++k) { edm += s_red[k]; step = fmax(step, s_red2[k]); }
+
+    if (allow_refresh == 1) {
+        const bool slow = edm > s.refresh_ratio * s.EDMPREV[toy];
+        const bool forced = s.force[toy] != 0;
+        const bool fresh = s.need_dir[toy] == 1;  // 2 = same point, damping raised after a rejection
+        const bool want = fresh && (forced || (s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm));
+        if (want) {
+            if (tid == 0) {
+                s.refresh[toy] = (!forced && edm < s.exact_below) ? 2 : 1;
+                s.force[toy] = 0;
+                s.EDM[toy] = edm;
+                const int k = atomicAdd(&s.counters[0], 1);
+                s.rlist[k] = (int)toy;
+            }
+            return;
+        }
+    } else if (allow_refresh == 0) {
+        if (s.refresh[toy] == 2 && (!(edm <= 100.0 * s.EDM[toy] + 1.0) || step > 100.0)) {
+            if (tid == 0) {
+                s.refresh[toy] = 1;
+                const int k = atomicAdd(&s.counters[2], 1);
+                s.rlist2[k] = (int)toy;
+            }
+            return;
+        }
+    }
+    double* d = s.Dd + toy * P;
+    for (int p = tid; p < P; p += nth) d[p] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < nl; i += nth) d[loc[i]] = gl[i];
+    for (int a = tid; a < ng; a += nth) d[glb[a]] = r[a];
+    if (tid == 0) {
+        s.EDM[toy] = edm;
+        s.EDMPREV[toy] = edm;
+        s.T[toy] = 1.0;
+        s.need_dir[toy] = 0;
+        if (!isfinite(edm)) { s.done[toy] = 1; s.status[toy] = 2; }
+        else if (edm < s.tol_edm && step < s.tol_step) { s.done[toy] = 1; s.status[toy] = 0; }
+    }
+}
+
 __global__ void fit_mark_own_kernel(FitDev s, const int* __restrict__ list, int64_t nlist) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < nlist) s.own[list[r]] = 1;
@@ -392,17 +634,16 @@ __global__ void fit_mark_own_kernel(FitDev s, const int* __restrict__ list, int6
 // ---------------------------------------------------------------- trial point / acceptance
 // compact trial points of the live fits: XTc[k] = clip(X + T*D) of fit live[k]
 __global__ void fit_trial_kernel(FitDev s, const int* __restrict__ live, int64_t nl,
-                                 double* __restrict__ XTc, int* __restrict__ ridx, int64_t toy0,
-                                 int64_t data_rows) {
+                                 double* __restrict__ XTc, int* __restrict__ ridx) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nl * s.P) return;
     const int64_t k = idx / s.P;
     const int p = (int)(idx - k * s.P);
     const int64_t toy = live[k];
     double v = s.X[toy * s.P + p];
-    if (!s.done[toy] && !s.fixed[p]) v = fmin(fmax(v + s.T[toy] * s.Dd[toy * s.P + p], s.lo[p]), s.hi[p]);
+    if (!s.done[toy] && !fit_mask(s, toy)[p]) v = fmin(fmax(v + s.T[toy] * s.Dd[toy * s.P + p], s.lo[p]), s.hi[p]);
     XTc[idx] = v;
-    if (p == 0) ridx[k] = (data_rows == 1) ? 0 : (int)(toy0 + toy);
+    if (p == 0) ridx[k] = (int)fit_data_row(s, toy);
 }
 
 // one warp per live fit; fits that stay alive are appended to live_next
@@ -426,7 +667,12 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
     const double slack = 4e-15 * fmax(1.0, fabs(f));
     const bool ok = isfinite(ft) && (ft <= f + kArmijo * dec + slack);
     bool alive = true;
+    if (s.trace && (nl <= 3 || toy < 2) && lane == 0)
+        printf("[hf_fit trace] fit %lld it %d f %.12g ft-f %.3e dec %.3e edm %.3e damp %.3e own %d refresh %d nfail %d %s\n",
+               (long long)toy, s.niter[toy], f, ft - f, dec, s.EDM[toy], s.damp[toy], s.own[toy], s.refresh[toy],
+               s.nfail[toy], ok ? "accept" : "reject");
     if (ok) {
+        if (lane == 0) atomicAdd(&s.counters[3], 1);
         for (int p = lane; p < P; p += 32) {
             s.X[toy * P + p] = xt[p];
             s.G[toy * P + p] = -2.0 * GTc[k * P + p];
@@ -532,10 +778,16 @@ void build_fd_structure(hf_plan* plan) {
 int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const double* init,
                   int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
                   int64_t N, const hf_fit_opts* opts_in, double* x_out, double* fun_out,
-                  int32_t* status_out, int32_t* niter_out, cudaStream_t st) {
+                  int32_t* status_out, int32_t* niter_out, cudaStream_t st,
+                  const uint8_t* fixed_alt, const uint8_t* use_alt, const int32_t* data_map) {
     if (N <= 0) return HF_OK;
-    if ((data_rows != 1 && data_rows != N) || (init_rows != 1 && init_rows != N)) {
-        hf_set_error("data_rows/init_rows must be 1 or N");
+    if ((!data_map && data_rows != 1 && data_rows != N) || data_rows < 1 ||
+        (init_rows != 1 && init_rows != N)) {
+        hf_set_error("data_rows/init_rows must be 1 or N (data_rows is free when a data map is given)");
+        return HF_ERR_INVALID;
+    }
+    if ((fixed_alt == nullptr) != (use_alt == nullptr)) {
+        hf_set_error("fixed_alt and use_alt must be given together");
         return HF_ERR_INVALID;
     }
     hf_fit_opts opts;
@@ -545,9 +797,12 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     build_fd_structure(plan);
 
     // ---- column structure for this fixed mask (host: P is small)
-    std::vector<uint8_t> h_fixed(P);
+    // (a parameter gets no FD column only when it is fixed under every mask of the batch)
+    std::vector<uint8_t> h_fixed(P), h_alt(P, 1);
     HF_CUDA_OK(cudaMemcpyAsync(h_fixed.data(), fixed, P, cudaMemcpyDeviceToHost, st));
+    if (fixed_alt) HF_CUDA_OK(cudaMemcpyAsync(h_alt.data(), fixed_alt, P, cudaMemcpyDeviceToHost, st));
     HF_CUDA_OK(cudaStreamSynchronize(st));
+    for (int p = 0; p < P; ++p) h_fixed[p] = (h_fixed[p] && h_alt[p]) ? 1 : 0;
     std::vector<int32_t> colpar, pcolor(P), pcol(P, -1);
     std::vector<char> color_used(std::max(plan->fd_ncolors, 1), 0);
     for (int p = 0; p < P; ++p) {
@@ -581,7 +836,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     Carver cv{nullptr};
     auto carve = [&](Carver& c, FitDev& s, double*& XP, double*& GP, double*& VP, double*& DR,
                      double*& AS, double*& XG, int*& ridx, int*& d_colpar, int*& d_pcolor,
-                     int*& d_partner, int*& d_pcol, int*& d_islocal) {
+                     int*& d_partner, int*& d_pcol, int*& d_islocal, uint8_t*& d_struct) {
         s.X = c.take<double>(NC * P); s.G = c.take<double>(NC * P); s.Dd = c.take<double>(NC * P);
         s.XT = c.take<double>(NC * P); s.GT = c.take<double>(NC * P); s.VT = c.take<double>(NC);
         s.F = c.take<double>(NC); s.T = c.take<double>(NC); s.EDM = c.take<double>(NC);
@@ -594,6 +849,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.nfail = c.take<int>(NC); s.force = c.take<int>(NC); s.rlist2 = c.take<int>(NC + 1);
         s.damp = c.take<double>(NC);
         d_islocal = c.take<int>(P);
+        d_struct = c.take<uint8_t>(P);
         XP = c.take<double>((size_t)max_pts * P); GP = c.take<double>((size_t)max_pts * P);
         VP = c.take<double>(max_pts); DR = c.take<double>((size_t)rl_cap * D);
         AS = c.take<double>((size_t)rl_cap * D);
@@ -606,7 +862,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     memset(&s, 0, sizeof(s));
     double *XP, *GP, *VP, *DR, *AS, *XG;
     int *ridx, *d_colpar, *d_pcolor, *d_partner, *d_pcol, *d_islocal;
-    carve(cv, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal);
+    uint8_t* d_struct;
+    carve(cv, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal, d_struct);
     const size_t need = cv.off + 4096;
     if (need > plan->fit_bytes) {
         if (plan->fit_block) cudaFree(plan->fit_block);
@@ -620,10 +877,13 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         plan->fit_bytes = need;
     }
     Carver cv2{(char*)plan->fit_block};
-    carve(cv2, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal);
+    carve(cv2, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal, d_struct);
     s.P = P; s.D = D; s.ncol = ncol; s.nglob = nglob; s.ncolors = std::max(ncolors, 1);
     s.colpar = d_colpar; s.pcolor = d_pcolor; s.partner = d_partner; s.pcol = d_pcol;
     s.lo = lo; s.hi = hi; s.fixed = fixed;
+    s.fixed_alt = fixed_alt; s.use_alt = use_alt; s.fixed_struct = d_struct; s.data_map = data_map;
+    s.data_rows = data_rows; s.toy0 = 0;
+    HF_CUDA_OK(cudaMemcpyAsync(d_struct, h_fixed.data(), P, cudaMemcpyHostToDevice, st));
     s.chol_in_smem = chol_in_smem ? 1 : 0;
     s.islocal = d_islocal;
     s.use_local = (plan->fd_ncolors == 1) ? 1 : 0;  // locals never share a bin: their block is diagonal
@@ -635,6 +895,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     }
     s.tol_edm = opts.tol_edm; s.tol_step = opts.tol_step; s.refresh_ratio = 0.05; s.exact_below = 10.0;
     s.max_iter = opts.max_iter;
+    s.trace = opts.verbose >= 3 ? 1 : 0;
     HF_CUDA_OK(cudaMemcpyAsync(d_colpar, colpar.data(), sizeof(int) * nglob, cudaMemcpyHostToDevice, st));
     HF_CUDA_OK(cudaMemcpyAsync(d_pcolor, pcolor.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
     HF_CUDA_OK(cudaMemcpyAsync(d_pcol, pcol.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
@@ -645,6 +906,34 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     const size_t dir_smem = dir_smem_small + (chol_in_smem ? tri_bytes : 0);
     HF_CUDA_OK(cudaFuncSetAttribute(fit_direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)dir_smem));
+    // Schur-form solver: only the global block is factorised (needs a diagonal local block)
+    const int sch_ng = std::max(nglob, 1), sch_nl = std::max(nfree - nglob, 1);
+    const int sch_ltile = std::min(sch_nl, sch_ng > 64 ? 16 : 32);
+    const int sch_threads = sch_ng <= 32 ? 64 : (sch_ng <= 96 ? 128 : 256);
+    const size_t sch_smem = sizeof(double) * ((size_t)sch_ng * (sch_ng + 1) / 2 + 3 * (size_t)sch_ng +
+                                              2 * (size_t)sch_nl + (size_t)sch_ltile * (sch_ng | 1)) +
+                            sizeof(int) * ((size_t)sch_ng + sch_nl) + 16;
+    const char* sch_env = getenv("HF_FIT_SCHUR");
+    const bool use_schur = plan->fd_ncolors <= 1 && sch_smem <= 220 * 1024 && !(sch_env && sch_env[0] == '0');
+    if (use_schur)
+        HF_CUDA_OK(cudaFuncSetAttribute(fit_direction_schur_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sch_smem));
+    auto launch_dir = [&](const int* lst, int64_t n, int mode) -> int {
+        if (use_schur) {
+            fit_direction_schur_kernel<<<(unsigned)n, sch_threads, sch_smem, st>>>(s, lst, n, mode, sch_ng,
+                                                                                   sch_nl, sch_ltile);
+            plan->launches++;
+            return HF_OK;
+        }
+        const int64_t dstep = chol_in_smem ? n : dir_grid_cap;
+        for (int64_t i0 = 0; i0 < n; i0 += dstep) {
+            const int64_t nb = std::min<int64_t>(dstep, n - i0);
+            fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, lst + i0, nb, mode);
+            plan->launches++;
+            if (!chol_in_smem) HF_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        return HF_OK;
+    };
 
     auto blocks = [](int64_t n, int t) { return (unsigned)((n + t - 1) / t); };
 
@@ -656,8 +945,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             fit_gather_x_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, lst, nl, XG);
             int rc = hf_expected_launch(plan, XG, nl, AS, st);
             if (rc) return rc;
-            fit_fd_rows_kernel<<<blocks(nl * D, 256), 256, 0, st>>>(s, lst, nl, mode, data, data_rows,
-                                                                    toy0, AS, DR);
+            fit_fd_rows_kernel<<<blocks(nl * D, 256), 256, 0, st>>>(s, lst, nl, mode, data, AS, DR);
             const int64_t npts = nl * (ncol + 1);
             fit_fd_points_kernel<<<blocks(npts * P, 256), 256, 0, st>>>(s, lst, nl, XP, ridx);
             plan->launches += 3;
@@ -678,11 +966,13 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     for (int64_t toy0 = 0; toy0 < N; toy0 += NC) {
         const int64_t nc = std::min<int64_t>(NC, N - toy0);
         s.NC = nc;
+        s.toy0 = toy0;
         const double* init_c = init + (init_rows == 1 ? 0 : toy0 * P);
-        const double* data_c = data + (data_rows == 1 ? 0 : toy0 * D);
+        const double* data_c = data + ((data_rows == 1 || data_map) ? 0 : toy0 * D);
         fit_init_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s, init_c, init_rows);
         plan->launches++;
-        int rc = hf_eval_launch(plan, s.X, data_c, data_rows == 1 ? 1 : nc, nc, s.VT, s.GT, st);
+        int rc = hf_eval_launch(plan, s.X, data_c, data_map ? data_rows : (data_rows == 1 ? 1 : nc), nc, s.VT,
+                                s.GT, st, data_map ? data_map + toy0 : nullptr);
         if (rc) return rc;
         fit_adopt_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s);
         plan->launches++;
@@ -705,13 +995,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             n_rounds++; n_dir += nl; n_evals += nl;
             HF_CUDA_OK(cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st));
             // ---- Newton directions of the live fits that accepted a step
-            const int64_t dir_step = chol_in_smem ? nl : dir_grid_cap;
-            for (int64_t i0 = 0; i0 < nl; i0 += dir_step) {
-                const int64_t nb = std::min<int64_t>(dir_step, nl - i0);
-                fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, s.live + i0, nb, 1);
-                plan->launches++;
-                if (!chol_in_smem) HF_CUDA_OK(cudaStreamSynchronize(st));
-            }
+            rc = launch_dir(s.live, nl, 1);
+            if (rc) return rc;
             HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
             HF_CUDA_OK(cudaStreamSynchronize(st));
             const int nrefresh = h_counters[0];
@@ -724,12 +1009,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                 // mark ownership, recompute the directions of the refreshed fits
                 fit_mark_own_kernel<<<blocks(nrefresh, 256), 256, 0, st>>>(s, s.rlist, nrefresh);
                 plan->launches++;
-                for (int64_t i0 = 0; i0 < nrefresh; i0 += dir_step) {
-                    const int64_t nb = std::min<int64_t>(dir_step, nrefresh - i0);
-                    fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, s.rlist + i0, nb, 0);
-                    plan->launches++;
-                    if (!chol_in_smem) HF_CUDA_OK(cudaStreamSynchronize(st));
-                }
+                rc = launch_dir(s.rlist, nrefresh, 0);
+                if (rc) return rc;
                 // fits whose exact Hessian turned out unusable: Fisher matrix instead
                 HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
                 HF_CUDA_OK(cudaStreamSynchronize(st));
@@ -737,19 +1018,15 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                 if (nfall > 0) {
                     rc = run_hessians(s.rlist2, nfall, s.refresh, toy0, 0);
                     if (rc) return rc;
-                    for (int64_t i0 = 0; i0 < nfall; i0 += dir_step) {
-                        const int64_t nb = std::min<int64_t>(dir_step, nfall - i0);
-                        fit_direction_kernel<<<(unsigned)nb, kDirThreads, dir_smem, st>>>(s, s.rlist2 + i0, nb, -1);
-                        plan->launches++;
-                        if (!chol_in_smem) HF_CUDA_OK(cudaStreamSynchronize(st));
-                    }
+                    rc = launch_dir(s.rlist2, nfall, -1);
+                    if (rc) return rc;
                 }
             }
             if (prof) { double t1 = tick(); t_dir2 += t1 - t0; t0 = t1; }
             // ---- one trial point per live fit, evaluated as one compact K2 batch
-            fit_trial_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, s.live, nl, s.XT, ridx, toy0, data_rows);
+            fit_trial_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, s.live, nl, s.XT, ridx);
             plan->launches++;
-            rc = hf_eval_launch(plan, s.XT, data, data_rows == 1 ? 1 : N, nl, s.VT, s.GT, st, ridx);
+            rc = hf_eval_launch(plan, s.XT, data, data_rows, nl, s.VT, s.GT, st, ridx);
             if (rc) return rc;
             if (prof) { double t1 = tick(); t_eval += t1 - t0; t0 = t1; }
             HF_CUDA_OK(cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st));
@@ -757,7 +1034,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             plan->launches++;
             HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
             HF_CUDA_OK(cudaStreamSynchronize(st));
-            if (opts.verbose) fprintf(stderr, "[hf_fit] round %d: live %lld refresh %d -> live %d\n", round, (long long)nl, nrefresh, h_counters[1]);
+            if (opts.verbose) fprintf(stderr, "[hf_fit] round %d: live %lld refresh %d accepted %d -> live %d\n", round, (long long)nl, nrefresh, h_counters[3], h_counters[1]);
             nl = h_counters[1];
             std::swap(s.live, s.live_next);
             if (prof) { double t1 = tick(); t_acc += t1 - t0; t0 = t1; }

@@ -182,3 +182,32 @@ def test_sampler_moments_and_determinism(golden, cuda):
     s = batched.sample_poisson(_B(), rate, (40000,))
     assert torch.allclose(s.mean(0), rate, rtol=0.03)
     assert torch.allclose(s.var(0), rate, rtol=0.06)
+
+
+@pytest.mark.parametrize("name", ["mixed_code4p_code4", "c3"])
+def test_mixed_mask_batch_equals_separate_batches(name, golden, cuda):
+    """hf_fit_batch_mixed: constrained and free fits sharing data rows in ONE batch give the
+    results of the two separate batches (the minimum is unique to tolerance; paths may differ)."""
+    g = golden(name)
+    hp = g.host_plan()
+    plan = _dev_plan(g, cuda)
+    n = 24
+    toys = plan.sample_toys(hp.init, n, seed=5)
+    fp = torch.as_tensor(hp.fixed.copy(), device=cuda)
+    fp[hp.poi_index] = 1
+    init_f = plan.init.clone()
+    init_f[hp.poi_index] = 0.7
+    sep_f = plan.fit(toys, init_f, fixed=fp)
+    sep_u = plan.fit(toys)
+    rows = torch.arange(n, dtype=torch.int32, device=cuda).repeat(2)
+    use_alt = torch.cat([torch.ones(n), torch.zeros(n)]).to(torch.uint8).to(cuda)
+    init = torch.cat([init_f.expand(n, -1), plan.init.expand(n, -1)])
+    both = plan.fit(toys, init, fixed_alt=fp, use_alt=use_alt, data_map=rows)
+    assert int((both.status != 0).sum()) == 0
+    assert torch.all(both.x[:n, hp.poi_index] == 0.7)
+    np.testing.assert_allclose(both.fun[:n].cpu().numpy(), sep_f.fun.cpu().numpy(), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(both.fun[n:].cpu().numpy(), sep_u.fun.cpu().numpy(), rtol=0, atol=1e-7)
+    # the mapped data rows may come in any order and repeat
+    perm = torch.tensor([3, 3, 0, 7], dtype=torch.int32, device=cuda)
+    some = plan.fit(toys, data_map=perm)
+    np.testing.assert_allclose(some.fun.cpu().numpy(), sep_u.fun[perm.long()].cpu().numpy(), rtol=0, atol=1e-7)

@@ -9,7 +9,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 model = pyhf.Model(synth.spec_c3(), poi_name="mu", validate=False)
 hp = extract_plan(model); plan = batched.DevicePlan(hp)
 toys = plan.sample_toys(hp.init, n, seed=11)
-batched.qmu_tilde_batch(plan, 1.0, toys[:64])
+batched.qmu_tilde_batch(plan, 1.0, toys)  # warm-up at full size (workspaces are sized on first use)
 torch.cuda.synchronize(); t0 = time.time()
 out = batched.qmu_tilde_batch(plan, 1.0, toys, verbose=int(os.environ.get("HF_VERBOSE", "0")))
 torch.cuda.synchronize(); dt = time.time() - t0

@@ -30,7 +30,7 @@ hp = extract_plan(model)
 np.random.seed(0)
 data = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(hp.init)).sample((1,))[0])
 plan = batched.DevicePlan(hp)
-dist.toy_hypotest_distributed(plan, args.mu, data, 256 * world, seed=3)  # warm-up
+dist.toy_hypotest_distributed(plan, args.mu, data, args.ntoys, seed=3)  # warm-up at full size: workspaces are sized on first use
 if world > 1:
     torch.distributed.barrier()
 torch.cuda.synchronize()
