@@ -112,17 +112,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count(self, t0, t1=float("inf")):
+        return sum(1 for t, _ in self.rows if t0 <= t <= t1)
+
+    def stop(self, t0=0.0, t1=float("inf")):
+        """summary of the samples taken in [t0, t1] (the sampler itself starts before the warm-up,
+        nvidia-smi needs a few hundred ms to come up)"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names)
-                   if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+                   if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
@@ -266,15 +272,16 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     fp64_peak = batched.fp64_peak_tflops()
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
     plan.set_timing(True)
     launches0 = plan.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_load0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -284,7 +291,15 @@ def run_b200(args):
     launches = plan.launch_count - launches0
     main_ms, main_n = plan.main_kernel_ms()
     plan.set_timing(False)
-    clk = clocks.stop()
+    # a short timed region sees few 100 ms clock samples: keep the SAME load running (untimed)
+    # until there are at least 8 samples under load, 3 s at most
+    extra = 0
+    while clocks.proc is not None and clocks.count(t_load0) < 8 and time.time() - t_load0 < 3.0:
+        step()
+        torch.cuda.synchronize()
+        extra += 1
+    clk = clocks.stop(t_load0, time.time())
+    clk["window"] = f"timed region + {extra} further untimed steps of the same load"
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

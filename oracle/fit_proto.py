@@ -39,7 +39,7 @@ def fd_hessian(pl, x, data, free, g0=None, h=1e-5):
     return Hm
 
 
-def solve_reduced(Hm, g, act, damp=None):
+def solve_reduced(Hm, g, act, damp=None, max_step=None):
     """Newton direction on the non-active variables: (H_FF + tau I) d = -g_F, d_A = 0.
     tau starts at the fit's Levenberg-Marquardt damping and grows until the Cholesky
     factorisation succeeds (modified Newton)."""
@@ -61,6 +61,17 @@ def solve_reduced(Hm, g, act, damp=None):
                 tau = max(1e-10 * scale, tau * 10)
         z = np.linalg.solve(L, -g[i, f])
         di = np.linalg.solve(L.T, z)
+        if max_step is not None:
+            # trust-region flavour: a matrix that is barely positive definite after the shift gives
+            # a huge step along its soft direction; raise the shift until the step is bounded
+            for _ in range(40):
+                if np.max(np.abs(di)) <= max_step:
+                    break
+                tau = max(4.0 * tau, 1e-6 * scale)
+                L = np.linalg.cholesky(A + tau * np.eye(len(f)))
+                di = np.linalg.solve(L.T, np.linalg.solve(L, -g[i, f]))
+            if damp is not None:
+                damp[i] = max(damp[i], 0.0 if tau < 1e-6 * scale else tau)
         d[i, f] = di
         edm[i] = -g[i, f] @ di
     return d, edm
@@ -68,7 +79,7 @@ def solve_reduced(Hm, g, act, damp=None):
 
 def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_step=1e-7,
               refresh_ratio=0.05, exact_below=10.0, verbose=False, rho_damping=False, damp0=0.0,
-              damp0_edm=np.inf, rho_hi=np.inf, rho_hi_fac=0.2):
+              damp0_edm=np.inf, rho_hi=np.inf, rho_hi_fac=0.2, max_step=None):
     data = np.atleast_2d(data)
     init = np.atleast_2d(init)
     N = max(data.shape[0], init.shape[0])
@@ -106,7 +117,10 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
         if len(rows):
             xr, gr = x[rows], g[rows]
             act = fixed[None, :] | ((xr <= lo) & (gr > 0)) | ((xr >= hi) & (gr < 0))
-            dd, edm = solve_reduced(Hm[rows], gr, act, damp[rows])
+            dmp = damp[rows].copy()
+            dd, edm = solve_reduced(Hm[rows], gr, act, dmp, max_step)
+            if max_step is not None:
+                damp[rows] = dmp
             if it == 0 and damp0 > 0.0:
                 # start-up: a huge predicted decrease means the start point is far outside the
                 # quadratic regime; begin with a damped step instead of discovering it by rejections
@@ -130,10 +144,15 @@ def fit_batch(pl, data, init, lo, hi, fixed, max_iter=100, tol_edm=1e-10, tol_st
                 Hm[rr] = fd_hessian(pl, x[rr], dd_rows, free)
                 own[rr] = True
                 n_hess += len(rr)
-                dd2, edm2 = solve_reduced(Hm[rr], g[rr], act[refresh], damp[rr])
+                dmp = damp[rr].copy()
+                dd2, edm2 = solve_reduced(Hm[rr], g[rr], act[refresh], dmp, max_step)
+                if max_step is not None:
+                    damp[rr] = dmp
                 # a nearly singular / indefinite exact Hessian shows up as an exploding step:
                 # fall back to the Fisher matrix for this iteration
                 blow = exact & (~(edm2 <= 100.0 * edm[refresh] + 1.0) | (np.max(np.abs(dd2), axis=1) > 100.0))
+                if max_step is not None:
+                    blow &= False
                 if np.any(blow):
                     rb = rr[blow]
                     Hm[rb] = fd_hessian(pl, x[rb], O.expected_data(pl, x[rb]), free)

@@ -342,14 +342,28 @@ def qmu_tilde_batch(plan: DevicePlan, mu, data, init=None, lo=None, hi=None, fix
 
 
 def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=0, init=None,
-                 lo=None, hi=None, fixed=None, mode="qtilde", gather=None, **fit_kw):
+                 lo=None, hi=None, fixed=None, mode="qtilde", gather=None, profile=None, **fit_kw):
     """Toy-based CLs for one signal strength: the arithmetic of ToyCalculator.distributions /
     pvalues (reference infer/calculators.py:754-915) with every fit batched on the device: the
     4 * ntoys toy fits (2 hypotheses x {POI fixed, free}) are one lock-step batch.
 
-    ``gather`` (optional) maps a per-rank [n] tensor to the all-rank tensor (see dist.py); toys
-    [toy_offset, toy_offset + ntoys) are this rank's shard."""
+    ``gather`` (optional) maps a per-rank [2, n] tensor to the all-rank [2, n_total] tensor (see dist.py); toys
+    [toy_offset, toy_offset + ntoys) are this rank's shard.  ``profile`` (optional dict) receives
+    the wall time of each phase (adds a device synchronisation per phase)."""
+    import time
+
     dev = plan.device
+
+    def mark(name, _t=[None]):
+        if profile is None:
+            return
+        torch.cuda.synchronize(dev)
+        now = time.perf_counter()
+        if _t[0] is not None:
+            profile[name] = profile.get(name, 0.0) + now - _t[0]
+        _t[0] = now
+
+    mark("start")
     data_obs = _dev_tensor(data_obs, dev).reshape(1, -1)
     init = plan.init if init is None else _dev_tensor(init, dev)
     fixed = plan.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
@@ -369,20 +383,26 @@ def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=
     muhat_obs = obs_u.x[:, poi].contiguous()
     qobs = teststat(obs_f.fun.contiguous(), obs_u.fun.contiguous(), muhat_obs, float(mu_test), mode)
     obs = dict(q=qobs, muhat=muhat_obs, fixed=obs_f, free=obs_u)
+    mark("observed_fits")
     toys = torch.empty(2 * ntoys, plan.D, dtype=F64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(plan._lib.hf_sample_toys(plan._h, _ptr(gen.x[0].contiguous()), int(seed), int(toy_offset),
                                             int(ntoys), _ptr(toys[:ntoys]), _stream()))
         _lib.check(plan._lib.hf_sample_toys(plan._h, _ptr(gen.x[1].contiguous()), int(seed) + 1, int(toy_offset),
                                             int(ntoys), _ptr(toys[ntoys:]), _stream()))
+    mark("sampling")
     qq = qmu_tilde_batch(plan, mu_test, toys, init, lo, hi, fixed, mode, **fit_kw)
-    q_sig, q_bkg = qq["q"][:ntoys].contiguous(), qq["q"][ntoys:].contiguous()
+    mark("toy_fits")
+    q2 = qq["q"].reshape(2, ntoys)
     if gather is not None:
-        q_sig, q_bkg = gather(q_sig), gather(q_bkg)
+        q2 = gather(q2)          # one collective for both hypotheses
+    q_sig, q_bkg = q2[0].contiguous(), q2[1].contiguous()
+    mark("gather")
     n_sb = pvalue_counts(q_sig, qobs)[0].item()
     n_b = pvalue_counts(q_bkg, qobs)[0].item()
     clsb = n_sb / q_sig.numel()
     clb = n_b / q_bkg.numel()
+    mark("pvalues")
     return dict(qobs=float(qobs[0]), CLsb=clsb, CLb=clb, CLs=(clsb / clb if clb > 0 else float("nan")),
                 q_sig=q_sig, q_bkg=q_bkg, obs=obs, gen=gen,
                 n_failed=int((qq["fixed"].status != 0).sum() + (qq["free"].status != 0).sum()))

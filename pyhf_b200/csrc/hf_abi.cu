@@ -231,6 +231,7 @@ void hf_plan_destroy(hf_plan* plan) {
     cudaFree(plan->table_block);
     cudaFree(plan->work_block);
     cudaFree(plan->dconst);
+    if (plan->h_counters) cudaFreeHost(plan->h_counters);
     cudaFree(plan->fit_block);
     cudaFree(plan->stage_block);
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);

@@ -416,7 +416,8 @@ __device__ __forceinline__ void tri_decode(int e, int& a, int& b) {
 }
 
 __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
-                                           int allow_refresh, int ngmax, int nlmax, int ltile) {
+                                           int allow_refresh, int ngmax, int nlmax, int ltile,
+                                           int backup) {
     extern __shared__ __align__(16) double sm[];
     const int P = s.P;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
@@ -434,6 +435,9 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
     double* W = gl + nlmax;                          // [ltile][ngp] staged H_gl
     int* glb = reinterpret_cast<int*>(W + (size_t)ltile * ngp);
     int* loc = glb + ngmax;
+    // copy of the reduced matrix before factorisation (when it fits): a retry with a larger shift
+    // then costs one small Cholesky instead of the whole reduction
+    double* S2 = reinterpret_cast<double*>(loc + ((nlmax + ngmax + 1) & ~1) - ngmax);
     __shared__ int s_ng, s_nl, s_bad;
     __shared__ double s_red[32], s_red2[32];
 
@@ -445,6 +449,7 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
     const uint8_t* mask = fit_mask(s, toy);
     if (tid < 32) {
         int nl_ = 0, ng_ = 0;
+#pragma unroll 4
         for (int p0 = 0; p0 < P; p0 += 32) {
             const int p = p0 + lane;
             int f = 0;
@@ -470,7 +475,20 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
     double tau = s.damp[toy];  // Levenberg-Marquardt damping carried by the fit (0 = pure Newton)
     double maxdiag = -1.0;
     bool ok = false;
+    int attempts = 0;
+    bool have_copy = false;
+    double tau_base = tau;  // shift inside the stored copy (and on the local block)
     for (int attempt = 0; attempt < 40 && !ok; ++attempt) {
+        ++attempts;
+        bool bad = false;
+        if (have_copy) {
+            // only the global block takes the extra shift: still a positive definite modification
+            for (int e = tid; e < npk; e += nth) S[e] = S2[e];
+            __syncthreads();
+            for (int a = tid; a < ng; a += nth) S[tri(a, a)] += tau - tau_base;
+            __syncthreads();
+        } else {
+        tau_base = tau;
         for (int i = tid; i < nl; i += nth) {
             const int l = loc[i];
             const double h = Hsrc[(int64_t)l * P + l] + tau;
@@ -486,9 +504,10 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         }
         for (int a = tid; a < ng; a += nth) r[a] = -g[glb[a]];
         __syncthreads();
-        bool bad = s_bad != 0;
+        bad = s_bad != 0;
         for (int l0 = 0; l0 < nl && !bad; l0 += ltile) {
             const int nt = min(ltile, nl - l0);
+#pragma unroll 4
             for (int e = tid; e < ng * nt; e += nth) {
                 const int a = e / nt, t = e - a * nt;
                 W[t * ngp + a] = Hsrc[(int64_t)glb[a] * P + loc[l0 + t]];
@@ -507,6 +526,11 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
                 r[a] += acc;
             }
             __syncthreads();
+        }
+        if (backup && !bad) {
+            for (int e = tid; e < npk; e += nth) S2[e] = S[e];
+            have_copy = true;
+        }
         }
         // right-looking Cholesky of S; the diagonal keeps the pivots, linv holds 1/L_kk
         for (int j = 0; j < ng && !bad; ++j) {
@@ -545,6 +569,7 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         if (tid == 0) { s.done[toy] = 1; s.status[toy] = 2; }
         return;
     }
+    if (tid == 0 && attempts > 1) atomicAdd(&s.counters[4], attempts - 1);
     // L z = r
     for (int k = 0; k < ng; ++k) {
         const double zk = r[k] * linv[k];
@@ -560,11 +585,22 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         __syncthreads();
     }
     // d_l = -(g_l + H_lg d_g) / (H_ll + tau)   (left in gl)
-    for (int i = tid; i < nl; i += nth) {
-        const int l = loc[i];
-        double acc = 0.0;
-        for (int a = 0; a < ng; ++a) acc = fma(Hsrc[(int64_t)glb[a] * P + l], r[a], acc);
-        gl[i] = -gl[i] - dinv[i] * acc;
+    {
+        // nsub threads share one local parameter (interleaved over a) when threads outnumber locals
+        int nsub = 1;
+        while (nsub < 8 && nl * nsub * 2 <= nth) nsub *= 2;
+        const int i = tid / nsub, sub = tid - (tid / nsub) * nsub;
+        for (int i0 = 0; i0 < nl; i0 += nth / nsub) {
+            const int ii = i0 + i;
+            double acc = 0.0;
+            if (ii < nl) {
+                const int l = loc[ii];
+#pragma unroll 8
+                for (int a = sub; a < ng; a += nsub) acc = fma(Hsrc[(int64_t)glb[a] * P + l], r[a], acc);
+            }
+            for (int o = nsub >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (ii < nl && sub == 0) gl[ii] = -gl[ii] - dinv[ii] * acc;
+        }
     }
     __syncthreads();
     // edm = -g_F . d_F ; step = max |d|
@@ -836,7 +872,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     Carver cv{nullptr};
     auto carve = [&](Carver& c, FitDev& s, double*& XP, double*& GP, double*& VP, double*& DR,
                      double*& AS, double*& XG, int*& ridx, int*& d_colpar, int*& d_pcolor,
-                     int*& d_partner, int*& d_pcol, int*& d_islocal, uint8_t*& d_struct) {
+                     int*& d_partner, int*& d_pcol, int*& d_islocal, uint8_t*& d_struct, double*& DC) {
         s.X = c.take<double>(NC * P); s.G = c.take<double>(NC * P); s.Dd = c.take<double>(NC * P);
         s.XT = c.take<double>(NC * P); s.GT = c.take<double>(NC * P); s.VT = c.take<double>(NC);
         s.F = c.take<double>(NC); s.T = c.take<double>(NC); s.EDM = c.take<double>(NC);
@@ -850,6 +886,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.damp = c.take<double>(NC);
         d_islocal = c.take<int>(P);
         d_struct = c.take<uint8_t>(P);
+        DC = c.take<double>(data_rows);
         XP = c.take<double>((size_t)max_pts * P); GP = c.take<double>((size_t)max_pts * P);
         VP = c.take<double>(max_pts); DR = c.take<double>((size_t)rl_cap * D);
         AS = c.take<double>((size_t)rl_cap * D);
@@ -863,7 +900,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     double *XP, *GP, *VP, *DR, *AS, *XG;
     int *ridx, *d_colpar, *d_pcolor, *d_partner, *d_pcol, *d_islocal;
     uint8_t* d_struct;
-    carve(cv, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal, d_struct);
+    double* DC;
+    carve(cv, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal, d_struct, DC);
     const size_t need = cv.off + 4096;
     if (need > plan->fit_bytes) {
         if (plan->fit_block) cudaFree(plan->fit_block);
@@ -877,7 +915,19 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         plan->fit_bytes = need;
     }
     Carver cv2{(char*)plan->fit_block};
-    carve(cv2, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal, d_struct);
+    carve(cv2, s, XP, GP, VP, DR, AS, XG, ridx, d_colpar, d_pcolor, d_partner, d_pcol, d_islocal, d_struct, DC);
+    // theta-independent terms of every data row, once for the whole fit (every round evaluates
+    // trial points against this same array)
+    struct HeldConst {
+        hf_plan* p;
+        ~HeldConst() { p->dconst_held = nullptr; p->dconst_held_data = nullptr; p->dconst_held_rows = 0; }
+    } held{plan};
+    {
+        int rc0 = hf_data_const_launch(plan, data, data_rows, DC, st);
+        if (rc0) return rc0;
+        plan->dconst_held = DC; plan->dconst_held_data = data; plan->dconst_held_rows = data_rows;
+    }
+    if (!plan->h_counters) HF_CUDA_OK(cudaHostAlloc((void**)&plan->h_counters, sizeof(int32_t) * 16, cudaHostAllocDefault));
     s.P = P; s.D = D; s.ncol = ncol; s.nglob = nglob; s.ncolors = std::max(ncolors, 1);
     s.colpar = d_colpar; s.pcolor = d_pcolor; s.partner = d_partner; s.pcol = d_pcol;
     s.lo = lo; s.hi = hi; s.fixed = fixed;
@@ -908,11 +958,24 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                                     (int)dir_smem));
     // Schur-form solver: only the global block is factorised (needs a diagonal local block)
     const int sch_ng = std::max(nglob, 1), sch_nl = std::max(nfree - nglob, 1);
-    const int sch_ltile = std::min(sch_nl, sch_ng > 64 ? 16 : 32);
-    const int sch_threads = sch_ng <= 32 ? 64 : (sch_ng <= 96 ? 128 : 256);
-    const size_t sch_smem = sizeof(double) * ((size_t)sch_ng * (sch_ng + 1) / 2 + 3 * (size_t)sch_ng +
-                                              2 * (size_t)sch_nl + (size_t)sch_ltile * (sch_ng | 1)) +
-                            sizeof(int) * ((size_t)sch_ng + sch_nl) + 16;
+    // two launch shapes: "bulk" (thousands of fits: small CTAs, small staging tile, many CTAs per
+    // SM) and "latency" (the lock-step tail: a handful of fits, everything in flight at once)
+    struct SchurCfg { int threads, ltile, backup; size_t smem; };
+    auto schur_cfg = [&](bool bulk) {
+        SchurCfg c;
+        c.ltile = std::min(sch_nl, sch_ng > 64 ? 16 : 32);
+        if (!bulk && sizeof(double) * (size_t)sch_nl * (sch_ng | 1) <= 24 * 1024) c.ltile = sch_nl;
+        c.threads = bulk ? (sch_ng <= 32 ? 64 : (sch_ng <= 96 ? 128 : 512)) : (sch_ng <= 96 ? 256 : 512);
+        const size_t base = sizeof(double) * ((size_t)sch_ng * (sch_ng + 1) / 2 + 3 * (size_t)sch_ng +
+                                              2 * (size_t)sch_nl + (size_t)c.ltile * (sch_ng | 1)) +
+                            sizeof(int) * ((size_t)sch_ng + sch_nl + 2) + 16;
+        const size_t copy = sizeof(double) * ((size_t)sch_ng * (sch_ng + 1) / 2);
+        c.backup = (base + copy <= 64 * 1024) ? 1 : 0;
+        c.smem = base + (c.backup ? copy : 0);
+        return c;
+    };
+    const SchurCfg cfg_bulk = schur_cfg(true), cfg_lat = schur_cfg(false);
+    const size_t sch_smem = std::max(cfg_bulk.smem, cfg_lat.smem);
     const char* sch_env = getenv("HF_FIT_SCHUR");
     const bool use_schur = plan->fd_ncolors <= 1 && sch_smem <= 220 * 1024 && !(sch_env && sch_env[0] == '0');
     if (use_schur)
@@ -920,8 +983,9 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sch_smem));
     auto launch_dir = [&](const int* lst, int64_t n, int mode) -> int {
         if (use_schur) {
-            fit_direction_schur_kernel<<<(unsigned)n, sch_threads, sch_smem, st>>>(s, lst, n, mode, sch_ng,
-                                                                                   sch_nl, sch_ltile);
+            const SchurCfg& c = (n >= 4096) ? cfg_bulk : cfg_lat;
+            fit_direction_schur_kernel<<<(unsigned)n, c.threads, c.smem, st>>>(s, lst, n, mode, sch_ng, sch_nl,
+                                                                                c.ltile, c.backup);
             plan->launches++;
             return HF_OK;
         }
@@ -960,7 +1024,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     };
 
     std::vector<int> h_list;
-    int h_counters[8];
+    int32_t* h_counters = plan->h_counters;
     const int max_rounds = opts.max_iter * 4 + 40;
 
     for (int64_t toy0 = 0; toy0 < N; toy0 += NC) {
@@ -987,7 +1051,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         plan->launches++;
         int64_t nl = nc;  // live fits
         double t_dir = 0, t_hess = 0, t_dir2 = 0, t_eval = 0, t_acc = 0;
-        int n_rounds = 0; long long n_dir = 0, n_ref = 0, n_evals = 0;
+        int n_rounds = 0; long long n_dir = 0, n_ref = 0, n_evals = 0, n_retry = 0;
         auto tick = [&]() { cudaStreamSynchronize(st); return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const bool prof = opts.verbose >= 2;
         for (int round = 0; round < max_rounds && nl > 0; ++round) {
@@ -1001,6 +1065,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             HF_CUDA_OK(cudaStreamSynchronize(st));
             const int nrefresh = h_counters[0];
             n_ref += nrefresh;
+            int retries = h_counters[4];
             if (prof) { double t1 = tick(); t_dir += t1 - t0; t0 = t1; }
             if (nrefresh > 0) {
                 rc = run_hessians(s.rlist, nrefresh, s.refresh, toy0, 0);
@@ -1015,6 +1080,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                 HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
                 HF_CUDA_OK(cudaStreamSynchronize(st));
                 const int nfall = h_counters[2];
+                retries = h_counters[4];
                 if (nfall > 0) {
                     rc = run_hessians(s.rlist2, nfall, s.refresh, toy0, 0);
                     if (rc) return rc;
@@ -1022,6 +1088,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                     if (rc) return rc;
                 }
             }
+            n_retry += retries;
             if (prof) { double t1 = tick(); t_dir2 += t1 - t0; t0 = t1; }
             // ---- one trial point per live fit, evaluated as one compact K2 batch
             fit_trial_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, s.live, nl, s.XT, ridx);
@@ -1041,8 +1108,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         }
         if (prof)
             fprintf(stderr, "[hf_fit] chunk of %lld fits: %d rounds, dir1 %.1f ms (%lld), hessians %.1f ms (%lld), dir2 %.1f ms, "
-                            "trial+eval %.1f ms (%lld), accept %.1f ms\n", (long long)nc, n_rounds, 1e3 * t_dir, n_dir,
-                    1e3 * t_hess, n_ref, 1e3 * t_dir2, 1e3 * t_eval, n_evals, 1e3 * t_acc);
+                            "trial+eval %.1f ms (%lld), accept %.1f ms, factorisation retries %lld\n", (long long)nc, n_rounds, 1e3 * t_dir, n_dir,
+                    1e3 * t_hess, n_ref, 1e3 * t_dir2, 1e3 * t_eval, n_evals, 1e3 * t_acc, n_retry);
         fit_finish_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s, toy0, x_out, fun_out, status_out, niter_out);
         plan->launches++;
         HF_CUDA_OK(cudaGetLastError());

@@ -203,6 +203,12 @@ struct hf_plan {
     int64_t work_ld = 0;       // points capacity
     int64_t dconst_cap = 0;
     double* dconst = nullptr;
+    // data constants computed once by a caller that evaluates the same data array many times
+    // (the fit loop): hf_eval_launch skips hf_data_const_kernel when (data, rows) match
+    const double* dconst_held_data = nullptr;
+    int64_t dconst_held_rows = 0;
+    const double* dconst_held = nullptr;
+    int32_t* h_counters = nullptr;  // pinned host mirror of the fit loop's device counters
     // fit workspace
     void* fit_block = nullptr;
     size_t fit_bytes = 0;
@@ -231,6 +237,7 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
                    int64_t B, double* out, double* grad, cudaStream_t st,
                    const int* row_idx = nullptr);
 int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out, cudaStream_t st);
+int hf_data_const_launch(hf_plan* plan, const double* data, int64_t rows, double* out, cudaStream_t st);
 // DMMA main kernel (hf_eval_mma.cu); returns HF_ERR_UNSUPPORTED when the plan does not qualify
 int hf_main_mma_launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_point,
                        const int* row_idx, bool grad, cudaStream_t st);

@@ -12,7 +12,7 @@ import os
 
 import torch
 
-__all__ = ["shard_range", "init_from_env", "all_gather_1d", "toy_hypotest_distributed"]
+__all__ = ["shard_range", "init_from_env", "all_gather_1d", "all_gather_cols", "toy_hypotest_distributed"]
 
 
 def shard_range(n, rank, world):
@@ -41,23 +41,46 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
-def all_gather_1d(t, n_total=None):
-    """Concatenate every rank's 1-D shard in rank order (shards as produced by shard_range)."""
+def all_gather_cols(t, n_total=None):
+    """Concatenate every rank's [k, n_local] shard along the last axis, in rank order (shards as
+    produced by shard_range).  ONE collective: with ``n_total`` given the shard sizes follow from
+    shard_range and need no exchange; equal-size slots are padded to the largest shard."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return t
     world = dist.get_world_size()
-    n_local = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local)
-    counts = [int(c) for c in counts]
+    squeeze = t.dim() == 1
+    t2 = t.reshape(1, -1) if squeeze else t
+    k, n_local = t2.shape
+    if n_total is not None:
+        counts = [shard_range(n_total, r, world)[1] for r in range(world)]
+        if counts[dist.get_rank()] != n_local:
+            raise RuntimeError(f"rank shard has {n_local} items, shard_range says {counts[dist.get_rank()]}")
+    else:
+        mine = torch.tensor([n_local], dtype=torch.int64, device=t.device)
+        allc = torch.empty(world, dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(allc, mine)
+        counts = allc.tolist()
     pad = max(counts)
-    buf = torch.zeros(pad, dtype=t.dtype, device=t.device)
-    buf[: t.numel()] = t
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf)
-    out = torch.cat([p[:c] for p, c in zip(parts, counts)])
+    if pad == n_local:
+        buf = t2.contiguous()
+    else:
+        buf = torch.zeros(k, pad, dtype=t.dtype, device=t.device)
+        buf[:, :n_local] = t2
+    flat = torch.empty(world * k * pad, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(flat, buf.reshape(-1))
+    out = flat.reshape(world, k, pad)
+    if all(c == pad for c in counts):
+        res = out.permute(1, 0, 2).reshape(k, world * pad)
+    else:
+        res = torch.cat([out[r, :, :c] for r, c in enumerate(counts)], dim=1)
+    return res.reshape(-1) if squeeze else res
+
+
+def all_gather_1d(t, n_total=None):
+    """1-D convenience form of all_gather_cols."""
+    out = all_gather_cols(t, n_total)
     if n_total is not None and out.numel() != n_total:
         raise RuntimeError(f"gathered {out.numel()} items, expected {n_total}")
     return out
@@ -76,4 +99,4 @@ def toy_hypotest_distributed(plan, mu_test, data_obs, ntoys, seed=0, **kw):
         rank, world = 0, 1
     start, count = shard_range(ntoys, rank, world)
     return batched.toy_hypotest(plan, mu_test, data_obs, count, seed=seed, toy_offset=start,
-                                gather=lambda t: all_gather_1d(t, ntoys), **kw)
+                                gather=lambda t: all_gather_cols(t, ntoys), **kw)

@@ -39,6 +39,13 @@ def _worker(rank, world, port, n):
     start, count = shard_range(n, rank, world)
     got = all_gather_1d(full[start:start + count].clone(), n)
     assert torch.equal(got, full)
+    # the two hypotheses' statistics travel as one [2, n_local] block; also without n_total
+    from pyhf_b200.dist import all_gather_cols
+
+    two = torch.stack([full, -full])
+    got2 = all_gather_cols(two[:, start:start + count].clone(), n)
+    assert torch.equal(got2, two)
+    assert torch.equal(all_gather_cols(two[:, start:start + count].clone()), two)
     # p-value arithmetic of EmpiricalDistribution.pvalue on the gathered array is rank-independent
     assert float((got >= 3.0).double().mean()) == float((full >= 3.0).double().mean())
     dist.barrier()
