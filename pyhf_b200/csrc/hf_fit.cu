@@ -1096,7 +1096,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             rc = hf_eval_launch(plan, s.XT, data, data_rows, nl, s.VT, s.GT, st, ridx);
             if (rc) return rc;
             if (prof) { double t1 = tick(); t_eval += t1 - t0; t0 = t1; }
-            HF_CUDA_OK(cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st));
+            // (counters 1 and 3 are still zero from the memset at the top of the round)
             fit_accept_kernel<<<blocks(nl * 32, 256), 256, 0, st>>>(s, s.live, nl, s.XT, s.VT, s.GT, s.live_next);
             plan->launches++;
             HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
