@@ -15,7 +15,8 @@ from .compile import compile_spec  # noqa: F401
 def __getattr__(name):
     # device-side API is imported lazily so that ``import pyhf_b200`` works on a CPU-only box
     if name in ("DevicePlan", "plan_for", "qmu_tilde_batch", "toy_hypotest", "FitResult",
-                "teststat", "pvalue_counts", "fp64_peak_tflops"):
+                "teststat", "pvalue_counts", "fp64_peak_tflops", "asymptotic_scan",
+                "upper_limit_from_scan"):
         from . import batched
 
         return getattr(batched, name)

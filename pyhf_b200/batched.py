@@ -408,6 +408,105 @@ def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=
                 n_failed=int((qq["fixed"].status != 0).sum() + (qq["free"].status != 0).sum()))
 
 
+def asymptotic_scan(plan: DevicePlan, mus, data, init=None, lo=None, hi=None, fixed=None,
+                    test_stat="qtilde", calc_base_dist="normal", **fit_kw):
+    """Asymptotic CLs for a whole scan of POI values in TWO batched fit launches.
+
+    The reference runs AsymptoticCalculator.teststatistic (infer/calculators.py:345-456) once per
+    scan point: 5 fits each, 205 for the 41-point scan of upper_limits.py:148-213 -- of which only
+    2 * M + 3 are distinct (the free fit on the data, the Asimov-generating constrained fit and
+    the free fit on the Asimov data do not depend on the scan point).  Here:
+
+      batch 1 (M + 2 fits on the data):   free | POI fixed at asimov_mu | POI fixed at each mu
+      Asimov data = expected_data(constrained fit at asimov_mu)         (calculators.py:45-97)
+      batch 2 (M + 1 fits on the Asimov data):  free | POI fixed at each mu
+
+    followed by the arithmetic of teststatistic / pvalues / expected_pvalues
+    (calculators.py:416-445, :447-523) on M-element tensors.  Returns a dict of device tensors:
+    ``CLs_obs`` [M], ``CLs_exp`` [M, 5] (n_sigma = 2, 1, 0, -1, -2 as in the reference), ``CLsb``,
+    ``CLb``, ``qmu``, ``qmuA``, ``teststat``, ``muhat``, ``n_fits``.
+    """
+    if test_stat not in ("qtilde", "q", "q0"):
+        raise ValueError(f"unknown test statistic {test_stat}")
+    if calc_base_dist not in ("normal", "clipped_normal"):
+        raise ValueError(f"unknown base distribution for asymptotics {calc_base_dist}")
+    poi = plan.host.poi_index
+    if poi < 0:
+        raise ValueError("the model has no POI")
+    dev = plan.device
+    mus = _dev_tensor(mus, dev).reshape(-1)
+    M = mus.numel()
+    data = _dev_tensor(data, dev).reshape(1, -1)
+    init = plan.init if init is None else _dev_tensor(init, dev).reshape(-1)
+    fixed = plan.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
+    fp = fixed.clone()
+    fp[poi] = 1
+    asimov_mu = 1.0 if test_stat == "q0" else 0.0
+
+    def batch(rows, with_asimov_fit):
+        k = 2 if with_asimov_fit else 1
+        x0 = init.expand(M + k, -1).clone()
+        x0[k:, poi] = mus
+        if with_asimov_fit:
+            x0[1, poi] = asimov_mu
+        use_alt = torch.ones(M + k, dtype=torch.uint8, device=dev)
+        use_alt[0] = 0
+        return plan.fit(rows, x0, lo, hi, fixed, fixed_alt=fp, use_alt=use_alt,
+                        data_map=torch.zeros(M + k, dtype=torch.int32, device=dev), **fit_kw)
+
+    r1 = batch(data, True)
+    asimov = plan.expected_data(r1.x[1:2])
+    r2 = batch(asimov.reshape(1, -1), False)
+
+    def q_of(free_fun, free_mu, fixed_fun):
+        q = torch.clamp(fixed_fun - free_fun, min=0.0)           # test_statistics.py:56
+        if test_stat == "q0":
+            return torch.where(free_mu < 0.0, torch.zeros_like(q), q)   # :507-520
+        return torch.where(free_mu > mus, torch.zeros_like(q), q)       # :57-60
+
+    qmu = q_of(r1.fun[0], r1.x[0, poi], r1.fun[2:])
+    qmuA = q_of(r2.fun[0], r2.x[0, poi], r2.fun[1:])
+    # at mu == asimov_mu the Asimov data ARE the constrained-fit expectation, so both fits share
+    # their minimum and qmu_A = 0 identically; the two numerical minima differ by rounding
+    # (~1e-12), which the square root below would turn into 1e-6 on CLs
+    qmuA = torch.where(mus == asimov_mu, torch.zeros_like(qmuA), qmuA)
+    sq, sqA = torch.sqrt(qmu), torch.sqrt(qmuA)
+    if test_stat in ("q", "q0"):
+        ts = sq - sqA
+    else:
+        safe = torch.where(sqA == 0, torch.ones_like(sqA), sqA)
+        ts = torch.where((sq <= sqA) | (sqA == 0), sq - sqA, (qmu - qmuA) / (2.0 * safe))
+    ndtr = torch.special.ndtr
+    cutoff = -sqA if calc_base_dist == "clipped_normal" else torch.full_like(sqA, float("-inf"))
+    nan = torch.full_like(sqA, float("nan"))
+
+    def pvalues(t):
+        clsb = torch.where(t >= cutoff, ndtr(-(t + sqA)), nan)     # sb_dist.shift = -sqrt(qmuA)
+        clb = torch.where(t >= cutoff, ndtr(-t), nan)
+        return clsb, clb, clsb / clb
+
+    clsb, clb, cls = pvalues(ts)
+    exp = []
+    for nsig in (2.0, 1.0, 0.0, -1.0, -2.0):
+        t = torch.full_like(sqA, nsig)
+        t = torch.where(t > cutoff, t, cutoff)                      # b_dist.expected_value
+        exp.append(pvalues(t)[2])
+    status = torch.cat([r1.status, r2.status])
+    return dict(mu=mus, CLs_obs=cls, CLs_exp=torch.stack(exp, dim=1), CLsb=clsb, CLb=clb, qmu=qmu,
+                qmuA=qmuA, teststat=ts, muhat=r1.x[0, poi], asimov_data=asimov.reshape(-1),
+                fits_data=r1, fits_asimov=r2, n_fits=2 * M + 3, n_failed=int((status != 0).sum()))
+
+
+def upper_limit_from_scan(mus, cls, level=0.05):
+    """observed / expected limits by the interpolation of upper_limits.py:16-18
+    (``np.interp(level, cls[::-1], mus[::-1])`` on the scan)."""
+    mus = np.asarray(mus.detach().cpu() if hasattr(mus, "detach") else mus, dtype=float)
+    cls = np.asarray(cls.detach().cpu() if hasattr(cls, "detach") else cls, dtype=float)
+    if cls.ndim == 1:
+        return float(np.interp(level, cls[::-1], mus[::-1]))
+    return [float(np.interp(level, cls[::-1, i], mus[::-1])) for i in range(cls.shape[1])]
+
+
 def fp64_peak_tflops():
     lib = _lib.require()
     v = C.c_double(0.0)
