@@ -192,6 +192,11 @@ int hf_teststat(const double* fun_fixed, const double* fun_free, const double* m
  * counts[j] = #{ i : samples[i] >= values[j] }.  samples dev [N], values dev [M], counts dev [M] */
 int hf_pvalue_counts(const double* samples, int64_t N, const double* values, int64_t M,
                      int64_t* counts, void* stream);
+/* The same counts against samples SORTED ascending (binary search per value, O(M log N)): the
+ * path for ToyCalculator.expected_pvalues (infer/calculators.py:955-973), which asks for the
+ * p-values of every background-only toy -- O(N^2) in the reference. */
+int hf_pvalue_counts_sorted(const double* sorted_samples, int64_t N, const double* values, int64_t M,
+                            int64_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

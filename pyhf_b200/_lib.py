@@ -67,6 +67,7 @@ SIGNATURES = {
     "hf_sample_normal": (C.c_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp]),
     "hf_teststat": (C.c_int, [_vp, _vp, _vp, C.c_double, _i32, _i64, _vp, _vp]),
     "hf_pvalue_counts": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "hf_pvalue_counts_sorted": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

@@ -289,15 +289,56 @@ def teststat(fun_fixed, fun_free, muhat, mu, mode="qtilde"):
     return q
 
 
-def pvalue_counts(samples, values):
-    """#{samples >= value} per value (EmpiricalDistribution.pvalue, calculators.py:632-640)."""
+def pvalue_counts(samples, values, assume_sorted=False):
+    """#{samples >= value} per value (EmpiricalDistribution.pvalue, calculators.py:632-640).
+    Few values: one O(N M) sweep over the unsorted samples; many values (the expected band asks for
+    the p-values of every toy): sort once, then a binary search per value."""
     lib = _lib.require()
     samples = samples.contiguous()
     values = values.contiguous()
     counts = torch.empty(values.numel(), dtype=torch.int64, device=samples.device)
-    _lib.check(lib.hf_pvalue_counts(_ptr(samples), samples.numel(), _ptr(values), values.numel(),
-                                    _ptr(counts), _stream()))
+    if assume_sorted or values.numel() * samples.numel() > (1 << 24):
+        srt = samples if assume_sorted else torch.sort(samples).values
+        _lib.check(lib.hf_pvalue_counts_sorted(_ptr(srt), srt.numel(), _ptr(values), values.numel(),
+                                               _ptr(counts), _stream()))
+    else:
+        _lib.check(lib.hf_pvalue_counts(_ptr(samples), samples.numel(), _ptr(values), values.numel(),
+                                        _ptr(counts), _stream()))
     return counts
+
+
+_NORMAL_PERCENTILES = (2.27501319, 15.86552539, 50.0, 84.13447461, 97.72498681)  # calculators.py:966-968
+
+
+def _percentiles_sorted(srt, qs):
+    """numpy.percentile(..., method="linear") on an ascending 1-D device tensor"""
+    n = srt.numel()
+    pos = torch.as_tensor(qs, dtype=F64, device=srt.device) / 100.0 * (n - 1)
+    lo = torch.floor(pos).long().clamp_(0, n - 1)
+    hi = (lo + 1).clamp_(max=n - 1)
+    g = pos - lo.to(F64)
+    a, b = srt[lo], srt[hi]
+    # numpy's _lerp: a + (b - a) * g, evaluated from the far end for g >= 0.5
+    return torch.where(g >= 0.5, b - (b - a) * (1.0 - g), a + (b - a) * g)
+
+
+def empirical_expected_pvalues(q_sig, q_bkg):
+    """ToyCalculator.expected_pvalues (calculators.py:924-973): the p-values of EVERY
+    background-only toy under both empirical distributions, then the (-2..2 sigma) percentiles of
+    each.  O(N log N) (two sorts + binary searches) instead of the reference's O(N^2).
+    Returns (CLsb_exp, CLb_exp, CLs_exp), each a device tensor [5]."""
+    s_sig = torch.sort(q_sig.reshape(-1)).values
+    s_bkg = torch.sort(q_bkg.reshape(-1)).values
+    clsb = pvalue_counts(s_sig, s_bkg, assume_sorted=True).to(F64) / s_sig.numel()
+    clb = pvalue_counts(s_bkg, s_bkg, assume_sorted=True).to(F64) / s_bkg.numel()
+    cls = clsb / clb
+    return tuple(_percentiles_sorted(torch.sort(v).values, _NORMAL_PERCENTILES) for v in (clsb, clb, cls))
+
+
+def empirical_expected_value(samples, nsigma):
+    """EmpiricalDistribution.expected_value (calculators.py:642-699)"""
+    q = torch.special.ndtr(torch.as_tensor(nsigma, dtype=F64, device=samples.device).reshape(-1)) * 100.0
+    return _percentiles_sorted(torch.sort(samples.reshape(-1)).values, q)
 
 
 def _view(r: "FitResult", sl) -> "FitResult":
@@ -342,14 +383,17 @@ def qmu_tilde_batch(plan: DevicePlan, mu, data, init=None, lo=None, hi=None, fix
 
 
 def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=0, init=None,
-                 lo=None, hi=None, fixed=None, mode="qtilde", gather=None, profile=None, **fit_kw):
+                 lo=None, hi=None, fixed=None, mode="qtilde", gather=None, profile=None,
+                 return_expected_set=False, **fit_kw):
     """Toy-based CLs for one signal strength: the arithmetic of ToyCalculator.distributions /
     pvalues (reference infer/calculators.py:754-915) with every fit batched on the device: the
     4 * ntoys toy fits (2 hypotheses x {POI fixed, free}) are one lock-step batch.
 
     ``gather`` (optional) maps a per-rank [2, n] tensor to the all-rank [2, n_total] tensor (see dist.py); toys
     [toy_offset, toy_offset + ntoys) are this rank's shard.  ``profile`` (optional dict) receives
-    the wall time of each phase (adds a device synchronisation per phase)."""
+    the wall time of each phase (adds a device synchronisation per phase).
+    ``return_expected_set``: also the (-2..2 sigma) band of CLsb / CLb / CLs over the
+    background-only toys (``expected``), the O(N log N) form of calculators.py:924-973."""
     import time
 
     dev = plan.device
@@ -403,8 +447,12 @@ def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=
     clsb = n_sb / q_sig.numel()
     clb = n_b / q_bkg.numel()
     mark("pvalues")
+    expected = None
+    if return_expected_set:
+        expected = empirical_expected_pvalues(q_sig, q_bkg)
+        mark("expected_band")
     return dict(qobs=float(qobs[0]), CLsb=clsb, CLb=clb, CLs=(clsb / clb if clb > 0 else float("nan")),
-                q_sig=q_sig, q_bkg=q_bkg, obs=obs, gen=gen,
+                q_sig=q_sig, q_bkg=q_bkg, obs=obs, gen=gen, expected=expected,
                 n_failed=int((qq["fixed"].status != 0).sum() + (qq["free"].status != 0).sum()))
 
 

@@ -178,6 +178,23 @@ __global__ void pvalue_counts_kernel(const double* __restrict__ samples, int64_t
     if (j < M && c) atomicAdd(&counts[j], c);
 }
 
+// same counts against samples sorted ascending: N - lower_bound(value); O(M log N) instead of the
+// O(N M) sweep above (the reference is O(N^2) when every b-only toy gets its own p-values,
+// calculators.py:955-973)
+__global__ void pvalue_counts_sorted_kernel(const double* __restrict__ sorted, int64_t N,
+                                            const double* __restrict__ values, int64_t M,
+                                            long long* __restrict__ counts) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const double v = values[j];
+    int64_t lo = 0, hi = N;  // first index with sorted[i] >= v
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted[mid] >= v) hi = mid; else lo = mid + 1;
+    }
+    counts[j] = isnan(v) ? 0 : (N - lo);
+}
+
 // fp64 FMA pipe peak: 16 independent chains per thread, no memory traffic
 __global__ void fp64_peak_kernel(double* __restrict__ out, int iters, double seed) {
     double a[16];
@@ -282,6 +299,19 @@ int hf_pvalue_counts(const double* samples, int64_t N, const double* values, int
     const unsigned gx = (unsigned)((M + 255) / 256);
     unsigned gy = (unsigned)std::min<int64_t>((N + 1023) / 1024, std::max<int64_t>(1, 2368 / gx));
     pvalue_counts_kernel<<<dim3(gx, gy), 256, 0, st>>>(samples, N, values, M, (unsigned long long*)counts);
+    HF_CUDA_OK(cudaGetLastError());
+    return HF_OK;
+}
+
+int hf_pvalue_counts_sorted(const double* sorted_samples, int64_t N, const double* values, int64_t M,
+                            int64_t* counts, void* stream) {
+    if (!sorted_samples || !values || !counts) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    if (M <= 0) return HF_OK;
+    pvalue_counts_sorted_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        sorted_samples, N, values, M, (long long*)counts);
     HF_CUDA_OK(cudaGetLastError());
     return HF_OK;
 }
