@@ -166,6 +166,18 @@ int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,
                       int32_t* status_host, int32_t* niter_host, void* stream);
 
 /*
+ * Hessian of 2*NLL at B points: central differences of the analytic gradient (one-sided where a
+ * step would leave [lo, hi]), symmetrised; rows/columns of fixed parameters are the identity's.
+ * The covariance the reference gets from iminuit (optimize/opt_minuit.py:136-152, errordef = 1 on
+ * 2*NLL) is 2 * inverse(hess) on the free parameters; optimize/mixins.py:83-120 consumes it for
+ * return_uncertainties / return_correlations.
+ *   pars dev [B][P]; data dev [data_rows][D], data_rows in {1, B}; lo/hi dev [P]; fixed dev [P];
+ *   hess dev [B][P][P]
+ */
+int hf_hessian(hf_plan* plan, const double* pars, const double* data, int64_t data_rows, int64_t B,
+               const double* lo, const double* hi, const uint8_t* fixed, double* hess, void* stream);
+
+/*
  * K4 Philox-4x32-10 toy sampler: out[i] ~ Pois(lambda(pars)) (x) Normal(theta, sigma) (x)
  * Pois(theta*factor), i = 0..N-1, counter = (seed, offset + i) so results do not depend on how
  * toys are sharded over ranks.  Replaces Simultaneous.sample (probability.py:263-274) and

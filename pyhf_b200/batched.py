@@ -205,6 +205,50 @@ class DevicePlan:
                 _ptr(status), _ptr(niter), _stream()))
         return FitResult(x, fun, status, niter)
 
+    # ------------------------------------------------------------------ curvature
+    def hessian(self, pars, data, lo=None, hi=None, fixed=None):
+        """Hessian of 2*NLL at pars [B, P] (or [P]) by central differences of the analytic
+        gradient (hf_hessian); rows/columns of fixed parameters are the identity's."""
+        dev = self.device
+        pars = _dev_tensor(pars, dev)
+        single = pars.dim() == 1
+        if single:
+            pars = pars.reshape(1, -1)
+        data = _dev_tensor(data, dev)
+        if data.dim() == 1:
+            data = data.reshape(1, -1)
+        lo = self.lo if lo is None else _dev_tensor(lo, dev)
+        hi = self.hi if hi is None else _dev_tensor(hi, dev)
+        fixed = self.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)
+        B = pars.shape[0]
+        out = torch.empty(B, self.P, self.P, dtype=F64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.hf_hessian(self._h, _ptr(pars), _ptr(data), data.shape[0], B, _ptr(lo),
+                                            _ptr(hi), _ptr(fixed), _ptr(out), _stream()))
+        return out[0] if single else out
+
+    def covariance(self, pars, data, lo=None, hi=None, fixed=None):
+        """(covariance, uncertainties, correlations) of the parameters at a minimum: covariance =
+        2 * inverse(Hessian of 2*NLL) on the parameters that are free AND not on a bound (what
+        MINUIT reports with errordef = 1 on 2*NLL, reference optimize/opt_minuit.py:136-152); the
+        others get zero uncertainty (optimize/mixins.py:95-103) and zero correlation rows."""
+        dev = self.device
+        x = _dev_tensor(pars, dev).reshape(-1)
+        lo_t = self.lo if lo is None else _dev_tensor(lo, dev)
+        hi_t = self.hi if hi is None else _dev_tensor(hi, dev)
+        fx = (self.fixed if fixed is None else _dev_tensor(fixed, dev, torch.uint8)).bool()
+        H = self.hessian(x, data, lo, hi, fixed)
+        free = ~fx & (x > lo_t) & (x < hi_t)
+        idx = torch.nonzero(free).reshape(-1)
+        cov = torch.zeros(self.P, self.P, dtype=F64, device=dev)
+        if idx.numel():
+            sub = 2.0 * torch.linalg.inv(H[idx][:, idx])
+            cov[idx.unsqueeze(1), idx.unsqueeze(0)] = sub
+        unc = torch.sqrt(torch.clamp(torch.diagonal(cov), min=0.0))
+        denom = torch.where(unc > 0, unc, torch.ones_like(unc))
+        corr = cov / denom.unsqueeze(0) / denom.unsqueeze(1)
+        return cov, unc, corr
+
     # ------------------------------------------------------------------ toys
     def sample_toys(self, pars, n, seed=0, offset=0):
         """K4: n toys ~ Model.make_pdf(pars).sample((n,)) (reference probability.py:263-274)."""

@@ -111,11 +111,6 @@ class B200Optimizer:
                 "b200_optimizer minimises pyhf.infer.mle.twice_nll of a pyhf.Model on the GPU; "
                 "arbitrary Python objectives have no CPU fallback on this path"
             )
-        if return_correlations or return_uncertainties:
-            raise pyhf.exceptions.Unsupported(
-                "uncertainties/correlations are not provided by b200_optimizer (minuit-only in the "
-                "reference as well, optimize/mixins.py:83-120)"
-            )
         tensorlib, _ = pyhf.get_backend()
         try:
             plan = batched.plan_for(pdf)
@@ -162,11 +157,22 @@ class B200Optimizer:
                          unc=None, corr=None)
         if not result.success:  # optimize/mixins.py:64-68
             raise pyhf.exceptions.FailedMinimization(result)
+        if return_uncertainties or return_correlations:
+            # minuit-only in the reference (optimize/opt_minuit.py:136-152); here from the Hessian of
+            # 2*NLL at the minimum (hf_hessian).  Same output layout as optimize/mixins.py:83-120:
+            # x becomes [P, 2] = (value, uncertainty), fixed parameters get uncertainty 0
+            d_row = matrix[row] if toy is not None else d
+            _, unc, corr = plan.covariance(x, d_row, bounds[:, 0], bounds[:, 1], fixed)
+            result.unc, result.corr = unc, corr
+            if return_uncertainties:
+                result.x = torch.stack([result.x, unc], dim=1)
         if do_stitch:
             # the reference strips fixed parameters before and stitches them back after the fit
             # (optimize/common.py:108-125); the full vector is fitted here, nothing to stitch
             pass
         _returns = [result.x]
+        if return_correlations:
+            _returns.append(result.corr)
         if return_fitted_val:
             _returns.append(result.fun)
         if return_result_obj:
