@@ -297,8 +297,8 @@ int hf_ensure_work(hf_plan* plan, int64_t ld, int64_t data_rows) {
         w.dc1T = p; p += (int64_t)pl.H * ld;
         w.dc2T = p; p += (int64_t)pl.H * ld;
         w.FsegT = p; p += nq * ld;
-        w.GsegT = p; p += nq * ld;
-        w.gradT = p; p += (int64_t)pl.P * ld;
+        w.GsegT = p; p += nq * ld;               // GsegT | gradT | mainv stay adjacent: hf_eval_launch
+        w.gradT = p; p += (int64_t)pl.P * ld;     // clears the three accumulators with one memset
         w.mainv = p; p += ld;
         p = (double*)(((uintptr_t)p + 255) / 256 * 256);
         w.coefK = p;

@@ -740,10 +740,11 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
         hf_prep_kernel<<<grid, 128, (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, do_grad ? 1 : 0);
         plan->launches++;
     }
-    HF_CUDA_OK(cudaMemsetAsync(w.mainv, 0, sizeof(double) * ld, st));
+    // accumulators: GsegT | gradT | mainv are carved back to back (hf_ensure_work): one memset
     if (do_grad) {
-        HF_CUDA_OK(cudaMemsetAsync(w.gradT, 0, sizeof(double) * ld * pl.P, st));
-        HF_CUDA_OK(cudaMemsetAsync(w.GsegT, 0, sizeof(double) * ld * pl.S * pl.NSEG, st));
+        HF_CUDA_OK(cudaMemsetAsync(w.GsegT, 0, sizeof(double) * ld * ((size_t)pl.S * pl.NSEG + pl.P + 1), st));
+    } else {
+        HF_CUDA_OK(cudaMemsetAsync(w.mainv, 0, sizeof(double) * ld, st));
     }
     if (plan->dconst_held && plan->dconst_held_data == data && plan->dconst_held_rows == data_rows) {
         w.dconst = const_cast<double*>(plan->dconst_held);

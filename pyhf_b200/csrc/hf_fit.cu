@@ -105,11 +105,22 @@ __global__ void fit_adopt_kernel(FitDev s) {
 
 // ---------------------------------------------------------------- Hessian by finite differences
 // points of refresh entry r: r*(ncol+1) + c, c < ncol perturbed columns, c == ncol base point
+// (second part of the same grid: the data row of every entry, see fit_fd_rows)
+__device__ __forceinline__ void fit_fd_rows(const FitDev& s, const int* __restrict__ list, int64_t nlist,
+                                            const int* __restrict__ mode, const double* __restrict__ data,
+                                            const double* __restrict__ asimov, double* __restrict__ DR,
+                                            int64_t idx);
+
 __global__ void fit_fd_points_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
-                                     double* __restrict__ XP, int* __restrict__ row_idx) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                     double* __restrict__ XP, int* __restrict__ row_idx,
+                                     const int* __restrict__ mode, const double* __restrict__ data,
+                                     const double* __restrict__ asimov, double* __restrict__ DR) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t npts = nlist * (s.ncol + 1);
-    if (idx >= npts * s.P) return;
+    if (idx >= npts * s.P) {
+        fit_fd_rows(s, list, nlist, mode, data, asimov, DR, idx - npts * s.P);
+        return;
+    }
     const int64_t pt = idx / s.P;
     const int p = (int)(idx - pt * s.P);
     const int64_t r = pt / (s.ncol + 1);
@@ -126,11 +137,10 @@ __global__ void fit_fd_points_kernel(FitDev s, const int* __restrict__ list, int
 }
 
 // data row per refresh entry: Asimov (Fisher mode) or the fit's own data (exact mode)
-__global__ void fit_fd_rows_kernel(FitDev s, const int* __restrict__ list, int64_t nlist,
-                                   const int* __restrict__ mode, const double* __restrict__ data,
-                                   const double* __restrict__ asimov,
-                                   double* __restrict__ DR) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void fit_fd_rows(const FitDev& s, const int* __restrict__ list, int64_t nlist,
+                                            const int* __restrict__ mode, const double* __restrict__ data,
+                                            const double* __restrict__ asimov, double* __restrict__ DR,
+                                            int64_t idx) {
     if (idx >= nlist * s.D) return;
     const int64_t r = idx / s.D;
     const int j = (int)(idx - r * s.D);
@@ -278,7 +288,9 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     }
     __syncthreads();
     const int n = s_n, nloc = s_nloc;
-    const double* Hsrc = s.own[toy] ? (s.H + toy * (int64_t)P * P) : s.Hshared;
+    // (the pass after a refresh, allow_refresh != 1, is what makes the fit own its matrix)
+    const double* Hsrc = (s.own[toy] || allow_refresh != 1) ? (s.H + toy * (int64_t)P * P) : s.Hshared;
+    if (tid == 0 && allow_refresh != 1) s.own[toy] = 1;
 
     double maxdiag = 0.0;
     for (int i = tid; i < n; i += nth) maxdiag = fmax(maxdiag, fabs(Hsrc[(int64_t)fidx[i] * P + fidx[i]]));
@@ -366,7 +378,9 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
             if (tid == 0) {
                 // exact Hessian close to the minimum, Fisher matrix (PSD) far from it or after a
                 // failed line search
-                s.refresh[toy] = (!forced && edm < s.exact_below) ? 2 : 1;
+                const int kind = (!forced && edm < s.exact_below) ? 2 : 1;
+                s.refresh[toy] = kind;
+                if (kind == 1) atomicAdd(&s.counters[5], 1);  // Asimov rows needed this round
                 s.force[toy] = 0;
                 s.EDM[toy] = edm;  // estimate before the refresh (checked after it)
                 const int k = atomicAdd(&s.counters[0], 1);
@@ -443,7 +457,9 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
 
     const double* x = s.X + toy * P;
     const double* g = s.G + toy * P;
-    const double* Hsrc = s.own[toy] ? (s.H + toy * (int64_t)P * P) : s.Hshared;
+    // (the pass after a refresh, allow_refresh != 1, is what makes the fit own its matrix)
+    const double* Hsrc = (s.own[toy] || allow_refresh != 1) ? (s.H + toy * (int64_t)P * P) : s.Hshared;
+    if (tid == 0 && allow_refresh != 1) s.own[toy] = 1;
 
     // active set (box bounds, fixed parameters), compacted by one warp with ballots
     const uint8_t* mask = fit_mask(s, toy);
@@ -629,7 +645,9 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         const bool want = fresh && (forced || (s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm));
         if (want) {
             if (tid == 0) {
-                s.refresh[toy] = (!forced && edm < s.exact_below) ? 2 : 1;
+                const int kind = (!forced && edm < s.exact_below) ? 2 : 1;
+                s.refresh[toy] = kind;
+                if (kind == 1) atomicAdd(&s.counters[5], 1);  // Asimov rows needed this round
                 s.force[toy] = 0;
                 s.EDM[toy] = edm;
                 const int k = atomicAdd(&s.counters[0], 1);
@@ -660,11 +678,6 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         if (!isfinite(edm)) { s.done[toy] = 1; s.status[toy] = 2; }
         else if (edm < s.tol_edm && step < s.tol_step) { s.done[toy] = 1; s.status[toy] = 0; }
     }
-}
-
-__global__ void fit_mark_own_kernel(FitDev s, const int* __restrict__ list, int64_t nlist) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < nlist) s.own[list[r]] = 1;
 }
 
 // ---------------------------------------------------------------- trial point / acceptance
@@ -1002,17 +1015,21 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     auto blocks = [](int64_t n, int t) { return (unsigned)((n + t - 1) / t); };
 
     auto run_hessians = [&](const int* d_list, int64_t nlist, const int* mode, int64_t toy0,
-                            int to_shared) -> int {
+                            int to_shared, bool need_asimov = true) -> int {
         for (int64_t r0 = 0; r0 < nlist; r0 += rl_cap) {
             const int64_t nl = std::min<int64_t>(rl_cap, nlist - r0);
             const int* lst = d_list + r0;
-            fit_gather_x_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, lst, nl, XG);
-            int rc = hf_expected_launch(plan, XG, nl, AS, st);
-            if (rc) return rc;
-            fit_fd_rows_kernel<<<blocks(nl * D, 256), 256, 0, st>>>(s, lst, nl, mode, data, AS, DR);
+            int rc = HF_OK;
+            if (need_asimov) {  // Fisher entries: Asimov data of the entry's current point
+                fit_gather_x_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, lst, nl, XG);
+                plan->launches++;
+                rc = hf_expected_launch(plan, XG, nl, AS, st);
+                if (rc) return rc;
+            }
             const int64_t npts = nl * (ncol + 1);
-            fit_fd_points_kernel<<<blocks(npts * P, 256), 256, 0, st>>>(s, lst, nl, XP, ridx);
-            plan->launches += 3;
+            fit_fd_points_kernel<<<blocks(npts * P + nl * D, 256), 256, 0, st>>>(s, lst, nl, XP, ridx, mode,
+                                                                                  data, AS, DR);
+            plan->launches++;
             rc = hf_eval_launch(plan, XP, DR, nl, npts, VP, GP, st, ridx);
             if (rc) return rc;
             fit_fd_assemble_kernel<<<blocks(nl * (int64_t)P * P, 256), 256, 0, st>>>(
@@ -1068,12 +1085,10 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             int retries = h_counters[4];
             if (prof) { double t1 = tick(); t_dir += t1 - t0; t0 = t1; }
             if (nrefresh > 0) {
-                rc = run_hessians(s.rlist, nrefresh, s.refresh, toy0, 0);
+                rc = run_hessians(s.rlist, nrefresh, s.refresh, toy0, 0, h_counters[5] > 0);
                 if (rc) return rc;
                 if (prof) { double t1 = tick(); t_hess += t1 - t0; t0 = t1; }
-                // mark ownership, recompute the directions of the refreshed fits
-                fit_mark_own_kernel<<<blocks(nrefresh, 256), 256, 0, st>>>(s, s.rlist, nrefresh);
-                plan->launches++;
+                // recompute the directions of the refreshed fits (this pass marks ownership)
                 rc = launch_dir(s.rlist, nrefresh, 0);
                 if (rc) return rc;
                 // fits whose exact Hessian turned out unusable: Fisher matrix instead
