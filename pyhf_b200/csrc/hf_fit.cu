@@ -39,6 +39,7 @@ struct FitDev {
     double *X, *G, *Dd, *XT, *GT, *VT, *F, *T, *EDM, *EDMPREV, *H, *Hshared;
     int *done, *need_dir, *own, *status, *niter, *refresh, *rlist, *counters;
     int *nfail, *force, *rlist2;  // consecutive rejections, (unused), second request list
+    int* pending;  // fit waits for its Fisher fallback (computed at the top of the next round)
     double* damp;                 // Levenberg-Marquardt damping added to the diagonal (0 = pure Newton)
     int *live, *live_next;   // compacted list of fits still running (order is arbitrary)
     const int* islocal;      // [P] 1 when the parameter only couples to the global block (diagonal local block)
@@ -86,7 +87,7 @@ __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64
     if (p == 0) {
         s.done[i] = 0; s.need_dir[i] = 1; s.own[i] = 0; s.status[i] = 1; s.niter[i] = 0;
         s.refresh[i] = 0; s.T[i] = 1.0; s.EDM[i] = INFINITY; s.EDMPREV[i] = INFINITY;
-        s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = 0.0;
+        s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = 0.0; s.pending[i] = 0;
     }
 }
 
@@ -394,6 +395,7 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
         if (s.refresh[toy] == 2 && (!(edm <= 100.0 * s.EDM[toy] + 1.0) || step > 100.0)) {
             if (tid == 0) {
                 s.refresh[toy] = 1;
+                s.pending[toy] = 1;  // sits out this round's trial; served at the top of the next
                 const int k = atomicAdd(&s.counters[2], 1);
                 s.rlist2[k] = (int)toy;
             }
@@ -409,6 +411,7 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
         s.EDMPREV[toy] = edm;
         s.T[toy] = 1.0;
         s.need_dir[toy] = 0;
+        s.pending[toy] = 0;
         if (!isfinite(edm)) { s.done[toy] = 1; s.status[toy] = 2; }
         else if (edm < s.tol_edm && step < s.tol_step) { s.done[toy] = 1; s.status[toy] = 0; }
     }
@@ -659,6 +662,7 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         if (s.refresh[toy] == 2 && (!(edm <= 100.0 * s.EDM[toy] + 1.0) || step > 100.0)) {
             if (tid == 0) {
                 s.refresh[toy] = 1;
+                s.pending[toy] = 1;  // sits out this round's trial; served at the top of the next
                 const int k = atomicAdd(&s.counters[2], 1);
                 s.rlist2[k] = (int)toy;
             }
@@ -675,6 +679,7 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         s.EDMPREV[toy] = edm;
         s.T[toy] = 1.0;
         s.need_dir[toy] = 0;
+        s.pending[toy] = 0;
         if (!isfinite(edm)) { s.done[toy] = 1; s.status[toy] = 2; }
         else if (edm < s.tol_edm && step < s.tol_step) { s.done[toy] = 1; s.status[toy] = 0; }
     }
@@ -690,7 +695,7 @@ __global__ void fit_trial_kernel(FitDev s, const int* __restrict__ live, int64_t
     const int p = (int)(idx - k * s.P);
     const int64_t toy = live[k];
     double v = s.X[toy * s.P + p];
-    if (!s.done[toy] && !fit_mask(s, toy)[p]) v = fmin(fmax(v + s.T[toy] * s.Dd[toy * s.P + p], s.lo[p]), s.hi[p]);
+    if (!s.done[toy] && !s.pending[toy] && !fit_mask(s, toy)[p]) v = fmin(fmax(v + s.T[toy] * s.Dd[toy * s.P + p], s.lo[p]), s.hi[p]);
     XTc[idx] = v;
     if (p == 0) ridx[k] = (int)fit_data_row(s, toy);
 }
@@ -704,6 +709,10 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
     if (k >= nl) return;
     const int64_t toy = live[k];
     if (s.done[toy]) return;
+    if (s.pending[toy]) {  // no trial this round: stays alive, nothing else changes
+        if (lane == 0) live_next[atomicAdd(&s.counters[1], 1)] = (int)toy;
+        return;
+    }
     const int P = s.P;
     const double* x = s.X + toy * P;
     const double* xt = XTc + k * P;
@@ -896,6 +905,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.rlist = c.take<int>(NC + 1); s.counters = c.take<int>(8);
         s.live = c.take<int>(NC + 1); s.live_next = c.take<int>(NC + 1);
         s.nfail = c.take<int>(NC); s.force = c.take<int>(NC); s.rlist2 = c.take<int>(NC + 1);
+        s.pending = c.take<int>(NC);
         s.damp = c.take<double>(NC);
         d_islocal = c.take<int>(P);
         d_struct = c.take<uint8_t>(P);
@@ -1067,6 +1077,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         fit_iota_kernel<<<blocks(nc, 256), 256, 0, st>>>(s.live, nc);
         plan->launches++;
         int64_t nl = nc;  // live fits
+        int nfall = 0;    // Fisher fallbacks requested in the previous round
         double t_dir = 0, t_hess = 0, t_dir2 = 0, t_eval = 0, t_acc = 0;
         int n_rounds = 0; long long n_dir = 0, n_ref = 0, n_evals = 0, n_retry = 0;
         auto tick = [&]() { cudaStreamSynchronize(st); return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1074,6 +1085,15 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         for (int round = 0; round < max_rounds && nl > 0; ++round) {
             double t0 = prof ? tick() : 0.0;
             n_rounds++; n_dir += nl; n_evals += nl;
+            // fits whose exact Hessian turned out unusable last round: Fisher matrix instead
+            // (requested by the post-refresh direction pass, read back with last round's counts)
+            if (nfall > 0) {
+                rc = run_hessians(s.rlist2, nfall, s.refresh, toy0, 0);
+                if (rc) return rc;
+                rc = launch_dir(s.rlist2, nfall, -1);
+                if (rc) return rc;
+                nfall = 0;
+            }
             HF_CUDA_OK(cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st));
             // ---- Newton directions of the live fits that accepted a step
             rc = launch_dir(s.live, nl, 1);
@@ -1082,7 +1102,6 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             HF_CUDA_OK(cudaStreamSynchronize(st));
             const int nrefresh = h_counters[0];
             n_ref += nrefresh;
-            int retries = h_counters[4];
             if (prof) { double t1 = tick(); t_dir += t1 - t0; t0 = t1; }
             if (nrefresh > 0) {
                 rc = run_hessians(s.rlist, nrefresh, s.refresh, toy0, 0, h_counters[5] > 0);
@@ -1091,19 +1110,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                 // recompute the directions of the refreshed fits (this pass marks ownership)
                 rc = launch_dir(s.rlist, nrefresh, 0);
                 if (rc) return rc;
-                // fits whose exact Hessian turned out unusable: Fisher matrix instead
-                HF_CUDA_OK(cudaMemcpyAsync(h_counters, s.counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
-                HF_CUDA_OK(cudaStreamSynchronize(st));
-                const int nfall = h_counters[2];
-                retries = h_counters[4];
-                if (nfall > 0) {
-                    rc = run_hessians(s.rlist2, nfall, s.refresh, toy0, 0);
-                    if (rc) return rc;
-                    rc = launch_dir(s.rlist2, nfall, -1);
-                    if (rc) return rc;
-                }
             }
-            n_retry += retries;
             if (prof) { double t1 = tick(); t_dir2 += t1 - t0; t0 = t1; }
             // ---- one trial point per live fit, evaluated as one compact K2 batch
             fit_trial_kernel<<<blocks(nl * P, 256), 256, 0, st>>>(s, s.live, nl, s.XT, ridx);
@@ -1118,6 +1125,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             HF_CUDA_OK(cudaStreamSynchronize(st));
             if (opts.verbose) fprintf(stderr, "[hf_fit] round %d: live %lld refresh %d accepted %d -> live %d\n", round, (long long)nl, nrefresh, h_counters[3], h_counters[1]);
             nl = h_counters[1];
+            nfall = h_counters[2];
+            n_retry += h_counters[4];
             std::swap(s.live, s.live_next);
             if (prof) { double t1 = tick(); t_acc += t1 - t0; t0 = t1; }
         }
