@@ -409,7 +409,7 @@ def toy_fit_metric(batched, ntoys=100000):
     hp = compile_spec(synth.spec_c3(), poi_name="mu")  # == extract_plan(pyhf.Model(...)), tests/test_compile.py
     plan = batched.DevicePlan(hp)
     toys = plan.sample_toys(hp.init, ntoys, seed=11)
-    batched.qmu_tilde_batch(plan, 1.0, toys[:256])
+    batched.qmu_tilde_batch(plan, 1.0, toys)  # warm-up at full size: the fit workspace is sized on first use
     torch.cuda.synchronize()
     l0 = plan.launch_count
     t0 = time.perf_counter()

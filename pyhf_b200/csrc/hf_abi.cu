@@ -379,7 +379,12 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
     double* d_grad = grad_host ? d_out + B : nullptr;
     // Pipeline over chunks of points: H2D of chunk i+1, the kernels of chunk i and D2H of chunk
     // i-1 overlap (PCIe is full duplex); the copy streams are ordered against `st` by events.
-    const int64_t CH = 16384;
+    // Chunk = 3 full waves of the dominant kernel (one CTA of HF_MMA_M points per SM and wave):
+    // a 16384-point chunk is 3.46 waves on 148 SMs and pays for 4.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t CH = (int64_t)sms * HF_MMA_M * 3;
     if (B <= 2 * CH || data_rows != 1) {
         HF_CUDA_OK(cudaMemcpyAsync(d_pars, pars_host, sizeof(double) * n_pars, cudaMemcpyHostToDevice, st));
         HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * n_data, cudaMemcpyHostToDevice, st));
