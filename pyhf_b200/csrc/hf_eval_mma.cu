@@ -59,6 +59,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)
@@ -103,7 +106,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     double* coefs = reinterpret_cast<double*>(smem_raw);            // [MM][KS]
     double* tbuf = coefs + (size_t)MM * KS;                          // [NSTAGE][KC*CS]
     double* wfs = tbuf + NSTAGE * KC * CS;                           // [MM][CS]  Delta, then w*F
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs + MM * CS);     // [NSTAGE + 1]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs + MM * CS);     // full[NSTAGE] | coefs | empty[NSTAGE]
     int64_t* row_off = reinterpret_cast<int64_t*>(bars + 8);         // [MM]
     double* nd_s = reinterpret_cast<double*>(row_off + MM);          // [MM][BT+1] observed counts
     double* nom_s = nd_s + MM * (BT + 1);                            // [S][BT]    nominal of the tile
@@ -119,6 +122,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
 
     if (tid == 0) {
         for (int i = 0; i <= NSTAGE; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(&bars[NSTAGE + 1 + i], NTHR / 32);  // one arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -154,6 +158,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     auto issue_next = [&]() {  // thread 0 only
         if (issued < n_items) {
             const int tile = issued / per_tile, chunk = (issued % per_tile) % NCH;
+            // the buffer is free once every warp has arrived for the item that used it last
+            if (issued >= NSTAGE) mbar_wait(&bars[NSTAGE + 1 + issued % NSTAGE], ((issued / NSTAGE) - 1) & 1);
             uint64_t* bar = &bars[issued % NSTAGE];
             mbar_expect_tx(bar, CHUNK_BYTES);
             bulk_g2s(tbuf + (size_t)(issued % NSTAGE) * KC * CS,
@@ -213,9 +219,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                         for (int ni = 0; ni < 2; ++ni)
                             dmma884(facc[mi][ni][0], facc[mi][ni][1], a[mi], b[ni]);
                 }
+                // this warp is done with the buffer (no CTA-wide barrier: warps may run one chunk apart)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[NSTAGE + 1 + consumed % NSTAGE]);
                 ++consumed;
-                __syncthreads();  // everyone is done with this buffer before it is refilled
             }
+            // the previous tile's readers of wfs (its epilogue / backward product) are done
+            __syncthreads();
             // Delta fragments -> shared [point][cell]; lane owns point 8mi+g, bin 4*warp+2ni+(t>>1),
             // rows ra, ra+1 of every (mi, ni) tile
 #pragma unroll
@@ -413,8 +423,9 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                         dmma884(bacc[chunk][ni][0], bacc[chunk][ni][1], a, b);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[NSTAGE + 1 + consumed % NSTAGE]);
                 ++consumed;
-                __syncthreads();
             }
         }
     }
