@@ -62,6 +62,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)
@@ -95,7 +104,7 @@ __device__ __forceinline__ void cell_bf_grad(const DevPlan& pl, const Work& w, i
 }
 
 constexpr int SMAX = 8;  // samples handled by the register-resident per-(sample, segment) sums
-constexpr int NSTAGE = 2;  // table-chunk buffers in flight (42 KB each); 3 measured no faster
+constexpr int NSTAGE = 2;  // table-chunk buffers in flight (42 KB each); 3 measured no faster (also with mbarrier release)
 constexpr int NTHR = 256;  // 8 warps: forward = 16 cells each, backward = (8 points) x (64 cells) each
 
 template <int NCH, bool GRAD, bool HASBF>
@@ -108,12 +117,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     double* wfs = tbuf + NSTAGE * KC * CS;                           // [MM][CS]  Delta, then w*F
     uint64_t* bars = reinterpret_cast<uint64_t*>(wfs + MM * CS);     // full[NSTAGE] | coefs | empty[NSTAGE]
     int64_t* row_off = reinterpret_cast<int64_t*>(bars + 8);         // [MM]
-    double* nd_s = reinterpret_cast<double*>(row_off + MM);          // [MM][BT+1] observed counts
-    double* nom_s = nd_s + MM * (BT + 1);                            // [S][BT]    nominal of the tile
-    int* seg_s = reinterpret_cast<int*>(nom_s + SMAX * BT);          // [BT]
-    int* srow_s = seg_s + BT;                                        // [SMAX]     histosys row of a sample
-    int* bfany_s = srow_s + SMAX;                                    // [BT]  bin carries a per-bin factor
-    int* bf_s = bfany_s + BT;                                        // [K][S][BT] per-bin factor indices
+    // tile constants, double buffered: tile i+1 is fetched (cp.async) while tile i is worked on
+    double* nd_s2 = reinterpret_cast<double*>(row_off + MM);         // [2][MM][BT+1] observed counts
+    double* nom_s2 = nd_s2 + 2 * MM * (BT + 1);                      // [2][S][BT]    nominal of the tile
+    int* seg_s2 = reinterpret_cast<int*>(nom_s2 + 2 * SMAX * BT);    // [2][BT]
+    int* srow_s = seg_s2 + 2 * BT;                                   // [SMAX]     histosys row of a sample
+    int* bf_s2 = srow_s + SMAX;                                      // [2][K][S][BT] per-bin factor indices
+    const int bf_stride = pl.K * pl.S * BT;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int64_t pt0 = (int64_t)blockIdx.x * MM;
@@ -151,6 +161,24 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     int pos_smp[SMAX];
 #pragma unroll
     for (int q = 0; q < SMAX; ++q) pos_smp[q] = srow_s[q];
+    auto prefetch_tile = [&](int tile) {  // all threads; completion: cp_async_wait_all + barrier
+        const int b0 = tile * BT, buf = tile & 1;
+        double* nom_d = nom_s2 + buf * SMAX * BT;
+        int* bf_d = bf_s2 + buf * bf_stride;
+        for (int i = tid; i < pl.S * BT; i += NTHR) {
+            const int s = i / BT, bl = i - s * BT;
+            cp_async8(&nom_d[i], &pl.nominal[(int64_t)s * pl.NB + min(b0 + bl, pl.NB - 1)]);
+        }
+        for (int i = tid; i < bf_stride; i += NTHR) {
+            const int ks = i / BT, bl = i - ks * BT;
+            cp_async4(&bf_d[i], &pl.bf_par[(int64_t)ks * pl.NB + min(b0 + bl, pl.NB - 1)]);
+        }
+        if (tid < BT) cp_async4(&seg_s2[buf * BT + tid], &pl.bin_seg[min(b0 + tid, pl.NB - 1)]);
+        // observed counts of the 32 points: a warp reads one point's 32 bins per pass
+        for (int q = warp; q < MM; q += NTHR / 32)
+            cp_async8(&nd_s2[(buf * MM + q) * (BT + 1) + lane], &data[row_off[q] + min(b0 + lane, pl.NB - 1)]);
+    };
+    prefetch_tile(0);
     int issued = 0;    // table chunks requested so far (thread 0)
     int consumed = 0;  // table chunks consumed so far (uniform)
     const int per_tile = (GRAD ? 2 : 1) * NCH;
@@ -239,30 +267,16 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     *reinterpret_cast<double2*>(&wfs[(size_t)(8 * mi + g) * CS + 4 * bl + ra]) = st;
                 }
         }
-        // ---- stage the tile's model constants in shared memory: one round of independent,
-        //      coalesced loads instead of a dependent global load chain per (bin, sample)
-        {
-            const int b0 = tile * BT;
-            for (int i = tid; i < S * BT; i += NTHR) {
-                const int s = i / BT, bl = i - s * BT;
-                nom_s[i] = pl.nominal[(int64_t)s * NB + min(b0 + bl, NB - 1)];
-            }
-            for (int i = tid; i < pl.K * S * BT; i += NTHR) {
-                const int ks = i / BT, bl = i - ks * BT;
-                bf_s[i] = pl.bf_par[(int64_t)ks * NB + min(b0 + bl, NB - 1)];
-            }
-            if (tid < BT) {
-                seg_s[tid] = pl.bin_seg[min(b0 + tid, NB - 1)];
-                int any = 0;
-                for (int ks = 0; ks < pl.K * S; ++ks) any |= (pl.bf_par[(int64_t)ks * NB + min(b0 + tid, NB - 1)] >= 0);
-                bfany_s[tid] = any;
-            }
-            // observed counts of the 32 points: a warp reads one point's 32 bins per pass
-            for (int q = warp; q < MM; q += NTHR / 32) {
-                nd_s[q * (BT + 1) + lane] = data[row_off[q] + min(b0 + lane, NB - 1)];
-            }
-        }
+        // ---- the tile's model constants were requested one tile ago (prefetch_tile): make them
+        //      visible, then request the next tile's into the other buffer (its last readers, the
+        //      epilogue of tile - 1, are past the barrier above)
+        cp_async_wait_all();
         __syncthreads();
+        if (tile + 1 < ntiles) prefetch_tile(tile + 1);
+        const double* nd_s = nd_s2 + (tile & 1) * MM * (BT + 1);
+        const double* nom_s = nom_s2 + (tile & 1) * SMAX * BT;
+        const int* seg_s = seg_s2 + (tile & 1) * BT;
+        const int* bf_s = bf_s2 + (tile & 1) * bf_stride;
 
         // ---------------------------------------------------------------- epilogue
         // positions 0..3 are the histosys rows (Delta in cell[0..3]), 4..7 the other samples.
@@ -285,8 +299,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             gseg = seg;
         };
         const int seg_first = seg_s[4 * warp], seg_last = seg_s[4 * warp + 3];
-        const bool plain = !HASBF || !(bfany_s[4 * warp] | bfany_s[4 * warp + 1] | bfany_s[4 * warp + 2] |
-                                       bfany_s[4 * warp + 3]);
+        bool plain = true;  // none of the warp's 4 bins carries a per-bin factor
+        if (HASBF) {
+            for (int ks = 0; ks < pl.K * S; ++ks) {
+                const int* r4 = bf_s + ks * BT + 4 * warp;
+                plain = plain && ((r4[0] & r4[1] & r4[2] & r4[3]) < 0);
+            }
+        }
         // bins are ordered, so the warp's 4 bins span at most two segments iff the inner ones
         // belong to the first or the last one; each segment gets one (masked) pass
         const bool two_seg = (seg_s[4 * warp + 1] == seg_first || seg_s[4 * warp + 1] == seg_last) &&
@@ -480,7 +499,8 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
     const DevPlan& pl = plan->d;
     const int KS = hf_mma_ks(pl.H);
     size_t smem = sizeof(double) * ((size_t)MM * KS + NSTAGE * KC * CS + MM * CS) + 64 + 8 * MM + 128 +
-                  sizeof(double) * (MM * (BT + 1) + SMAX * BT) + sizeof(int) * (2 * BT + SMAX + (size_t)pl.K * pl.S * BT);
+                  2 * sizeof(double) * (MM * (BT + 1) + SMAX * BT) +
+                  sizeof(int) * (2 * BT + SMAX + 2 * (size_t)pl.K * pl.S * BT) + 64;
     const int64_t half = KS / 2;
     hf_prep_mma_kernel<<<(unsigned)((ld * half + 255) / 256), 256, 0, st>>>(pl, plan->w, ld, KS);
     plan->launches++;
