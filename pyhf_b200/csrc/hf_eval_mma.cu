@@ -476,413 +476,6 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// hf_main_mma2_kernel: the same arithmetic, warp-specialised.  ncu on the kernel above
-// (profiles/r1_hf_main_mma_kernel_stalls.txt) shows the two DMMA phases running the tensor pipe
-// at its limit, but they are only 62 % of the samples: the epilogue (30 %) runs with the pipe
-// idle.  Here warps 0-3 do nothing but the two products and warps 4-7 nothing but the epilogue,
-// one bin tile behind:
-//
-//   MMA warps :  fwd(0) fwd(1) bwd(0) fwd(2) bwd(1) ... fwd(n-1) bwd(n-2) bwd(n-1)
-//   EPI warps :         epi(0)        epi(1)        ...                  epi(n-1)
-//
-// Delta / w*F tiles are double buffered in shared memory (wfs[tile & 1]); the hand-over goes
-// through mbarriers (delta_ready: 4 MMA-warp arrivals, wf_ready: 4 EPI-warp arrivals), the two
-// groups synchronise among themselves with named barriers.  4 warps saturate the fp64 tensor pipe
-// (tools/dmma_occ.cu).  forward: warp = 32 cells x 32 points (4x4 DMMA tiles); backward: warp =
-// 8 points x 128 cells x all K.
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-constexpr int NMW = 8;                  // MMA warps (two warpgroups); one more warpgroup does the epilogue
-constexpr int NEW_ = 4;                 // EPI warps
-constexpr int NTHR2 = (NMW + NEW_) * 32;
-
-template <int NCH, bool HASBF>
-__global__ void __launch_bounds__(NTHR2, 1)
-hf_main_mma2_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
-                    int per_point, const int* __restrict__ row_idx, int KS) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* coefs = reinterpret_cast<double*>(smem_raw);            // [MM][KS]
-    double* tbuf = coefs + (size_t)MM * KS;                          // [NSTAGE][KC*CS]
-    double* wfs2 = tbuf + NSTAGE * KC * CS;                          // [2][MM][CS]  Delta, then w*F
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs2 + 2 * MM * CS);
-    uint64_t* bar_full = bars;                       // [NSTAGE] table chunk landed
-    uint64_t* bar_coef = bars + NSTAGE;              // coefficient rows landed
-    uint64_t* bar_empty = bars + NSTAGE + 1;         // [NSTAGE] chunk buffer released (4 MMA warps)
-    uint64_t* bar_delta = bars + 2 * NSTAGE + 1;     // [2] Delta tile written (4 MMA warps)
-    uint64_t* bar_wf = bars + 2 * NSTAGE + 3;        // [2] w*F tile written (4 EPI warps)
-    int64_t* row_off = reinterpret_cast<int64_t*>(bars + 16);        // [MM]
-    double* nd_s2 = reinterpret_cast<double*>(row_off + MM);         // [2][MM][BT+1] observed counts
-    double* nom_s2 = nd_s2 + 2 * MM * (BT + 1);                      // [2][S][BT]
-    int* seg_s2 = reinterpret_cast<int*>(nom_s2 + 2 * SMAX * BT);    // [2][BT]
-    int* srow_s = seg_s2 + 2 * BT;                                   // [SMAX]
-    int* bf_s2 = srow_s + SMAX;                                      // [2][K][S][BT]
-    const int bf_stride = pl.K * pl.S * BT;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int64_t pt0 = (int64_t)blockIdx.x * MM;
-    const int NB = pl.NB, S = pl.S, ntiles = pl.mma_ntiles;
-    const double* tt = pl.mma_tt;
-
-    if (tid == 0) {
-        for (int i = 0; i <= NSTAGE; ++i) mbar_init(&bars[i], 1);
-        for (int i = 0; i < NSTAGE; ++i) mbar_init(&bar_empty[i], NMW);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_delta[i], NMW); mbar_init(&bar_wf[i], NEW_); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (tid < MM) {
-        int64_t pt = pt0 + tid;
-        if (pt >= B) pt = B - 1;
-        const int64_t row = row_idx ? (int64_t)row_idx[pt] : (per_point ? pt : 0);
-        row_off[tid] = row * pl.D;
-    }
-    if (tid < SMAX) {
-        int smp = -1;
-        if (tid < 4) {
-            if (tid < pl.R) smp = pl.hs_row_sample[tid];
-        } else {
-            int cnt = 0;
-            for (int s2 = 0; s2 < pl.S; ++s2)
-                if (pl.sample_hs_row[s2] < 0) {
-                    if (cnt == tid - 4) smp = s2;
-                    ++cnt;
-                }
-        }
-        srow_s[tid] = smp;
-    }
-    __syncthreads();
-
-    if (warp < NMW) {
-        // ======================================================================== MMA warps
-        // (384 threads x 168 registers fill the register file; ptxas does not re-budget the two
-        // roles around setmaxnreg, so no register hand-over between the warpgroups is attempted)
-        const int n_phases = 2 * ntiles, n_items = n_phases * NCH;
-        auto sched = [&](int ph, int& tile, bool& bwd) {
-            if (ph == 0) { tile = 0; bwd = false; }
-            else if (ph == n_phases - 1) { tile = ntiles - 1; bwd = true; }
-            else if (ph & 1) { tile = (ph + 1) >> 1; bwd = false; }
-            else { tile = (ph >> 1) - 1; bwd = true; }
-        };
-        int issued = 0, consumed = 0;
-        auto issue_next = [&]() {  // thread 0 only
-            if (issued < n_items) {
-                int tile; bool bwd;
-                sched(issued / NCH, tile, bwd);
-                const int chunk = issued % NCH;
-                if (issued >= NSTAGE) mbar_wait(&bar_empty[issued % NSTAGE], ((issued / NSTAGE) - 1) & 1);
-                uint64_t* bar = &bar_full[issued % NSTAGE];
-                mbar_expect_tx(bar, CHUNK_BYTES);
-                bulk_g2s(tbuf + (size_t)(issued % NSTAGE) * KC * CS,
-                         tt + ((size_t)tile * NCH + chunk) * KC * CS, CHUNK_BYTES, bar);
-            }
-            ++issued;
-        };
-        if (tid == 0) {
-            mbar_expect_tx(bar_coef, (uint32_t)(MM * KS * sizeof(double)));
-            bulk_g2s(coefs, w.coefK + pt0 * KS, (uint32_t)(MM * KS * sizeof(double)), bar_coef);
-            for (int i = 0; i < NSTAGE - 1; ++i) issue_next();
-        }
-        mbar_wait(bar_coef, 0);
-        double bacc[NCH][NT_BWD][2];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int n = 0; n < NT_BWD; ++n) bacc[c][n][0] = bacc[c][n][1] = 0.0;
-
-#pragma unroll 1
-        for (int ph = 0; ph < n_phases; ++ph) {
-            int tile; bool bwd;
-            sched(ph, tile, bwd);
-            double* wfs = wfs2 + (size_t)(tile & 1) * MM * CS;
-            if (!bwd) {
-                double facc[4][2][2];
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) facc[mi][ni][0] = facc[mi][ni][1] = 0.0;
-#pragma unroll 1
-                for (int chunk = 0; chunk < NCH; ++chunk) {
-                    if (tid == 0) issue_next();
-                    mbar_wait(&bar_full[consumed % NSTAGE], (consumed / NSTAGE) & 1);
-                    const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CS + 16 * warp + g;
-                    const double* ca = coefs + (size_t)g * KS + chunk * KC + t;
-#pragma unroll 5
-                    for (int k4 = 0; k4 < KC / 4; ++k4) {
-                        double a[4], b[2];
-#pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) a[mi] = ca[(size_t)(8 * mi) * KS + k4 * 4];
-#pragma unroll
-                        for (int ni = 0; ni < 2; ++ni) b[ni] = tb[(k4 * 4 + t) * CS + 8 * ni];
-#pragma unroll
-                        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                            for (int ni = 0; ni < 2; ++ni)
-                                dmma884(facc[mi][ni][0], facc[mi][ni][1], a[mi], b[ni]);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_empty[consumed % NSTAGE]);
-                    ++consumed;
-                }
-                // every MMA warp is past bwd(tile - 2), the last reader of this wfs buffer
-                named_bar_sync(1, NMW * 32);
-                // lane owns point 8mi+g, cells 16*warp + 8ni + 2t, +1
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) {
-                        double2 st;
-                        st.x = facc[mi][ni][0];
-                        st.y = facc[mi][ni][1];
-                        *reinterpret_cast<double2*>(&wfs[(size_t)(8 * mi + g) * CS + 16 * warp + 8 * ni + 2 * t]) = st;
-                    }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_delta[tile & 1]);
-            } else {
-                mbar_wait(&bar_wf[tile & 1], (tile >> 1) & 1);  // epilogue of this tile has written w*F
-#pragma unroll
-                for (int chunk = 0; chunk < NCH; ++chunk) {
-                    if (tid == 0) issue_next();
-                    mbar_wait(&bar_full[consumed % NSTAGE], (consumed / NSTAGE) & 1);
-                    // warp = (m-tile: points 8*(warp&3)+g) x (cell half: 64*(warp>>2) ..)
-                    const int c0 = 64 * (warp >> 2);
-                    const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CS + (size_t)g * CS + t + c0;
-                    const double* arow = wfs + (size_t)(8 * (warp & 3) + g) * CS + t + c0;
-#pragma unroll 4
-                    for (int c4 = 0; c4 < NC / 8; ++c4) {
-                        const double a = arow[4 * c4];
-#pragma unroll
-                        for (int ni = 0; ni < NT_BWD; ++ni) {
-                            const double b = tb[(size_t)(8 * ni) * CS + 4 * c4];
-                            dmma884(bacc[chunk][ni][0], bacc[chunk][ni][1], a, b);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_empty[consumed % NSTAGE]);
-                    ++consumed;
-                }
-            }
-        }
-        // flush: bacc[chunk][ni] = sums of (T1, T2) of modifier h for point 8*(warp&3)+g over this
-        // warp's half of the cells (the two halves add up in gradT)
-        const int64_t pw = pt0 + 8 * (warp & 3) + g;
-#pragma unroll
-        for (int chunk = 0; chunk < NCH; ++chunk)
-#pragma unroll
-            for (int ni = 0; ni < NT_BWD; ++ni) {
-                const int h = (chunk * KC + 8 * ni + 2 * t) >> 1;
-                if (h < pl.H) {
-                    const int par = pl.hs_par[h];
-                    double c1, c2, d1, d2;
-                    hf_hs_coeffs(pl.hs_code, w.parsT[(int64_t)par * ld + pw], c1, c2, d1, d2);
-                    atomicAdd(&w.gradT[(int64_t)par * ld + pw], d1 * bacc[chunk][ni][0] + d2 * bacc[chunk][ni][1]);
-                }
-            }
-        return;
-    }
-
-    // ============================================================================ EPI warps
-    const int ew = warp - NMW, etid = tid - NMW * 32;
-    int pos_smp[SMAX];
-#pragma unroll
-    for (int q = 0; q < SMAX; ++q) pos_smp[q] = srow_s[q];
-    auto prefetch_tile = [&](int tile) {
-        const int b0 = tile * BT, buf = tile & 1;
-        double* nom_d = nom_s2 + buf * SMAX * BT;
-        int* bf_d = bf_s2 + buf * bf_stride;
-        for (int i = etid; i < pl.S * BT; i += NEW_ * 32) {
-            const int s = i / BT, bl = i - s * BT;
-            cp_async8(&nom_d[i], &pl.nominal[(int64_t)s * pl.NB + min(b0 + bl, pl.NB - 1)]);
-        }
-        for (int i = etid; i < bf_stride; i += NEW_ * 32) {
-            const int ks = i / BT, bl = i - ks * BT;
-            cp_async4(&bf_d[i], &pl.bf_par[(int64_t)ks * pl.NB + min(b0 + bl, pl.NB - 1)]);
-        }
-        if (etid < BT) cp_async4(&seg_s2[buf * BT + etid], &pl.bin_seg[min(b0 + etid, pl.NB - 1)]);
-        for (int q = ew; q < MM; q += NEW_)
-            cp_async8(&nd_s2[(buf * MM + q) * (BT + 1) + lane], &data[row_off[q] + min(b0 + lane, pl.NB - 1)]);
-    };
-    prefetch_tile(0);
-    const int64_t p = pt0 + lane;
-    double val = 0.0;
-    double gacc[SMAX], fseg[SMAX];
-    int gseg = -1;
-#pragma unroll
-    for (int s = 0; s < SMAX; ++s) gacc[s] = fseg[s] = 0.0;
-    auto switch_segment = [&](int seg) {
-        if (gseg >= 0) {
-#pragma unroll
-            for (int q = 0; q < SMAX; ++q)
-                if (pos_smp[q] >= 0 && gacc[q] != 0.0)
-                    atomicAdd(&w.GsegT[((int64_t)pos_smp[q] * pl.NSEG + gseg) * ld + p], gacc[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < SMAX; ++q) {
-            gacc[q] = 0.0;
-            fseg[q] = (pos_smp[q] >= 0) ? w.FsegT[((int64_t)pos_smp[q] * pl.NSEG + seg) * ld + p] : 0.0;
-        }
-        gseg = seg;
-    };
-
-#pragma unroll 1
-    for (int tile = 0; tile < ntiles; ++tile) {
-        cp_async_wait_all();
-        named_bar_sync(2, NEW_ * 32);  // constants of this tile visible; every EPI warp is past epi(tile - 1)
-        if (tile + 1 < ntiles) prefetch_tile(tile + 1);
-        const double* nd_s = nd_s2 + (tile & 1) * MM * (BT + 1);
-        const double* nom_s = nom_s2 + (tile & 1) * SMAX * BT;
-        const int* seg_s = seg_s2 + (tile & 1) * BT;
-        const int* bf_s = bf_s2 + (tile & 1) * bf_stride;
-        double* wfs = wfs2 + (size_t)(tile & 1) * MM * CS;
-        mbar_wait(&bar_delta[tile & 1], (tile >> 1) & 1);  // Delta of this tile is in wfs
-
-#ifdef HF_DIAG_NO_EPI
-        if (tile >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&bar_wf[tile & 1]); continue; }
-#endif
-        // this warp: bins 8*ew .. 8*ew+7 of the tile in two groups of GB = 4, thread = point `lane`.
-        // Fast path (no per-bin factors, at most two segments): the bins of a group are interleaved
-        // dependency chains (8 at once measured slower than 4 + 4: 9.21 vs 9.05 ms).
-        constexpr int GB = 4;
-#pragma unroll 1
-        for (int half = 0; half < 8 / GB; ++half) {
-        const int bl0 = 8 * ew + GB * half;
-        const int seg_first = seg_s[bl0], seg_last = seg_s[bl0 + GB - 1];
-        bool plain = true, two_seg = true;
-        if (HASBF) {
-            for (int ks = 0; ks < pl.K * S; ++ks) {
-                const int* r = bf_s + ks * BT + bl0;
-#pragma unroll
-                for (int j = 0; j < GB; ++j) plain = plain && (r[j] < 0);
-            }
-        }
-#pragma unroll
-        for (int j = 1; j < GB - 1; ++j) two_seg = two_seg && (seg_s[bl0 + j] == seg_first || seg_s[bl0 + j] == seg_last);
-        if (plain && two_seg) {
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int seg_cur = pass ? seg_last : seg_first;
-                if (pass && seg_last == seg_first) break;
-                if (seg_cur != gseg) switch_segment(seg_cur);
-                double lam[GB], wgt[GB];
-                bool act[GB];
-#pragma unroll
-                for (int j = 0; j < GB; ++j) {
-                    const int bl = bl0 + j;
-                    act[j] = seg_s[bl] == seg_cur;
-                    const double4 dlt = *reinterpret_cast<const double4*>(wfs + (size_t)lane * CS + 4 * bl);
-                    const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
-                    double acc = 0.0;
-#pragma unroll
-                    for (int q = 0; q < SMAX; ++q) {
-                        if (pos_smp[q] >= 0) {
-                            double base = nom_s[pos_smp[q] * BT + bl];
-                            if (q < 4) base += dl[q];
-                            acc = fma(fseg[q], base, acc);
-                        }
-                    }
-                    lam[j] = acc;
-                }
-#pragma unroll
-                for (int j = 0; j < GB; ++j) {
-                    const int bl = bl0 + j;
-                    const bool valid = (tile * BT + bl < NB) && act[j];
-                    const double n = nd_s[lane * (BT + 1) + bl];
-#ifdef HF_DIAG_SKIP_EPI
-                    wgt[j] = valid ? n * lam[j] : 0.0;
-#else
-                    if (valid) val += hf_pois_term(n, lam[j]);
-                    wgt[j] = valid ? (n / lam[j] - 1.0) : 0.0;
-#endif
-                }
-#pragma unroll
-                for (int j = 0; j < GB; ++j) {
-                    if (!act[j]) continue;  // warp-uniform
-                    const int bl = bl0 + j;
-                    double* cell = wfs + (size_t)lane * CS + 4 * bl;
-                    const double4 dlt = *reinterpret_cast<const double4*>(cell);
-                    const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
-                    double wf[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                    for (int q = 0; q < SMAX; ++q) {
-                        if (pos_smp[q] >= 0) {
-                            double base = nom_s[pos_smp[q] * BT + bl];
-                            if (q < 4) base += dl[q];
-                            gacc[q] = fma(wgt[j], base, gacc[q]);
-                            if (q < 4) wf[q] = wgt[j] * fseg[q];
-                        }
-                    }
-                    double4 st;
-                    st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
-                    *reinterpret_cast<double4*>(cell) = st;
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < GB; ++j) {
-                const int bl = bl0 + j;
-                const int b = tile * BT + bl;
-                const bool valid = b < NB;
-                const int bb = valid ? b : NB - 1;
-                const int seg = seg_s[bl];
-                double* cell = wfs + (size_t)lane * CS + 4 * bl;
-                if (seg != gseg) switch_segment(seg);
-                const double4 dlt = *reinterpret_cast<const double4*>(cell);
-                double basev[SMAX], bfv[SMAX];
-                basev[0] = dlt.x; basev[1] = dlt.y; basev[2] = dlt.z; basev[3] = dlt.w;
-#pragma unroll
-                for (int q = 4; q < SMAX; ++q) basev[q] = 0.0;
-                double lam = 0.0;
-#pragma unroll
-                for (int q = 0; q < SMAX; ++q) {
-                    bfv[q] = 1.0;
-                    if (pos_smp[q] >= 0) {
-                        const int s = pos_smp[q];
-                        if (HASBF) {
-                            for (int k = 0; k < pl.K; ++k) {
-                                const int par = bf_s[(k * S + s) * BT + bl];
-                                if (par >= 0) bfv[q] *= w.parsT[(int64_t)par * ld + p];
-                            }
-                        }
-                        basev[q] += nom_s[s * BT + bl];
-                        lam = fma(fseg[q] * bfv[q], basev[q], lam);
-                    }
-                }
-                const double n = nd_s[lane * (BT + 1) + bl];
-                if (valid) val += hf_pois_term(n, lam);
-                const double wgt = valid ? (n / lam - 1.0) : 0.0;
-                double wf[4];
-#pragma unroll
-                for (int q = 0; q < SMAX; ++q) {
-                    if (pos_smp[q] >= 0) {
-                        const double wb = wgt * bfv[q];
-                        gacc[q] = fma(wb, basev[q], gacc[q]);
-                        if (q < 4) wf[q] = wb * fseg[q];
-                        if (HASBF && wgt != 0.0)
-                            cell_bf_grad(pl, w, ld, p, pos_smp[q], bb, wgt * fseg[q] * basev[q]);
-                    } else if (q < 4) {
-                        wf[q] = 0.0;
-                    }
-                }
-                double4 st;
-                st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
-                *reinterpret_cast<double4*>(cell) = st;
-            }
-        }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_wf[tile & 1]);  // this warp's 8 bins of w*F are in place
-    }
-    atomicAdd(&w.mainv[p], val);  // the four EPI warps hold different bins of the same points
-    if (gseg >= 0) {
-#pragma unroll
-        for (int q = 0; q < SMAX; ++q)
-            if (pos_smp[q] >= 0 && gacc[q] != 0.0)
-                atomicAdd(&w.GsegT[((int64_t)pos_smp[q] * pl.NSEG + gseg) * ld + p], gacc[q]);
-    }
-}
-
 // point-major coefficient rows for the A operand: coefK[pt][2h] = c1_h, [2h+1] = c2_h, zero padded
 __global__ void hf_prep_mma_kernel(DevPlan pl, Work w, int64_t ld, int KS) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -924,23 +517,12 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k<<<grid, NTHR, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS);              \
     }
-    static const bool use_v2 = getenv("HF_MMA2") && atoi(getenv("HF_MMA2")) != 0;  // experiment, off by default
-    const size_t smem2 = smem + sizeof(double) * MM * CS + 64;  // second Delta / w*F buffer
-#define HF_MMA2_GO(BF_)                                                                               \
-    {                                                                                                 \
-        auto k = hf_main_mma2_kernel<NCH, BF_>;                                                       \
-        HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-        k<<<grid, NTHR2, smem2, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS);              \
-    }
-    if (grad && use_v2 && smem2 <= 227 * 1024) {
-        if (pl.K > 0) HF_MMA2_GO(true) else HF_MMA2_GO(false)
-    } else if (grad) {
+    if (grad) {
         if (pl.K > 0) HF_MMA_GO(true, true) else HF_MMA_GO(true, false)
     } else {
         if (pl.K > 0) HF_MMA_GO(false, true) else HF_MMA_GO(false, false)
     }
 #undef HF_MMA_GO
-#undef HF_MMA2_GO
     if (plan->timing) {
         cudaEventRecord(e1, st);
         plan->ev.push_back(e0);
