@@ -114,8 +114,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* coefs = reinterpret_cast<double*>(smem_raw);            // [MM][KS]
     double* tbuf = coefs + (size_t)MM * KS;                          // [NSTAGE][KC*CS]
-    double* wfs = tbuf + NSTAGE * KC * CS;                           // [MM][CS]  Delta, then w*F
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs + MM * CS);     // full[NSTAGE] | coefs | empty[NSTAGE]
+    double* wfs2 = tbuf + NSTAGE * KC * CS;                          // [2][MM][CS]  Delta, then w*F
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs2 + 2 * MM * CS); // full[NSTAGE] | coefs | empty[NSTAGE]
     int64_t* row_off = reinterpret_cast<int64_t*>(bars + 8);         // [MM]
     // tile constants, double buffered: tile i+1 is fetched (cp.async) while tile i is worked on
     double* nd_s2 = reinterpret_cast<double*>(row_off + MM);         // [2][MM][BT+1] observed counts
@@ -221,6 +221,11 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     const int ra = 2 * (t & 1);
 
     for (int tile = 0; tile < ntiles; ++tile) {
+        // Delta / w*F of consecutive tiles alternate between two buffers: a warp that is ahead
+        // writes the next tile's Delta while a slow one still reads this tile's w*F in the
+        // backward product (the buffer it writes was last read two tiles ago, and two CTA
+        // barriers lie in between)
+        double* wfs = wfs2 + (size_t)(tile & 1) * MM * CS;
         // ---------------------------------------------------------------- forward contraction
         {
             double facc[4][2][2];
@@ -252,8 +257,6 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 if (lane == 0) mbar_arrive(&bars[NSTAGE + 1 + consumed % NSTAGE]);
                 ++consumed;
             }
-            // the previous tile's readers of wfs (its epilogue / backward product) are done
-            __syncthreads();
             // Delta fragments -> shared [point][cell]; lane owns point 8mi+g, bin 4*warp+2ni+(t>>1),
             // rows ra, ra+1 of every (mi, ni) tile
 #pragma unroll
@@ -498,7 +501,7 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
            const int* row_idx, bool grad, cudaStream_t st) {
     const DevPlan& pl = plan->d;
     const int KS = hf_mma_ks(pl.H);
-    size_t smem = sizeof(double) * ((size_t)MM * KS + NSTAGE * KC * CS + MM * CS) + 64 + 8 * MM + 128 +
+    size_t smem = sizeof(double) * ((size_t)MM * KS + NSTAGE * KC * CS + 2 * MM * CS) + 64 + 8 * MM + 128 +
                   2 * sizeof(double) * (MM * (BT + 1) + SMAX * BT) +
                   sizeof(int) * (2 * BT + SMAX + 2 * (size_t)pl.K * pl.S * BT) + 64;
     const int64_t half = KS / 2;
