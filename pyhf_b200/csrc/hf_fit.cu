@@ -58,7 +58,7 @@ struct FitDev {
     int64_t toy0, data_rows;      // first fit of the current chunk; rows of the data array
     double* chol_scratch;  // global-memory factor storage for n > smem capacity
     int chol_in_smem;
-    double tol_edm, tol_step, refresh_ratio, exact_below;
+    double tol_edm, tol_step, refresh_ratio, exact_below, damp0;
     int max_iter;
     int trace;  // verbose >= 3: print the state of the last few live fits every round
 };
@@ -87,7 +87,7 @@ __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64
     if (p == 0) {
         s.done[i] = 0; s.need_dir[i] = 1; s.own[i] = 0; s.status[i] = 1; s.niter[i] = 0;
         s.refresh[i] = 0; s.T[i] = 1.0; s.EDM[i] = INFINITY; s.EDMPREV[i] = INFINITY;
-        s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = 0.0; s.pending[i] = 0;
+        s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = s.damp0; s.pending[i] = 0;
     }
 }
 
@@ -967,6 +967,10 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         HF_CUDA_OK(cudaStreamSynchronize(st));  // isl goes out of scope
     }
     s.tol_edm = opts.tol_edm; s.tol_step = opts.tol_step; s.refresh_ratio = 0.05; s.exact_below = 10.0;
+    if (const char* e = getenv("HF_FIT_REFRESH")) s.refresh_ratio = atof(e);    // tuning knobs (tools/)
+    if (const char* e = getenv("HF_FIT_EXACT_BELOW")) s.exact_below = atof(e);
+    s.damp0 = 0.0;
+    if (const char* e = getenv("HF_FIT_DAMP0")) s.damp0 = atof(e);
     s.max_iter = opts.max_iter;
     s.trace = opts.verbose >= 3 ? 1 : 0;
     HF_CUDA_OK(cudaMemcpyAsync(d_colpar, colpar.data(), sizeof(int) * nglob, cudaMemcpyHostToDevice, st));
