@@ -158,9 +158,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         srow_s[tid] = smp;
     }
     __syncthreads();
-    int pos_smp[SMAX];
+    int pos_smp[SMAX], noff[SMAX], nother = 0;
 #pragma unroll
-    for (int q = 0; q < SMAX; ++q) pos_smp[q] = srow_s[q];
+    for (int q = 0; q < SMAX; ++q) {
+        pos_smp[q] = srow_s[q];
+        noff[q] = max(pos_smp[q], 0) * BT;          // row of the tile's nominal table
+        if (q >= 4 && pos_smp[q] >= 0) nother = q - 3;  // samples without histosys fill 4, 5, ...
+    }
     auto prefetch_tile = [&](int tile) {  // all threads; completion: cp_async_wait_all + barrier
         const int b0 = tile * BT, buf = tile & 1;
         double* nom_d = nom_s2 + buf * SMAX * BT;
@@ -327,11 +331,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     act[j] = seg_s[bl] == seg_cur;
                     const double4 dlt = *reinterpret_cast<const double4*>(wfs + (size_t)lane * CS + 4 * bl);
                     const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
+                    // positions without a sample carry fseg = 0 and read nominal row 0: no predicates
+                    // (only the rarely used positions 5..7 keep a uniform guard)
                     double acc = 0.0;
 #pragma unroll
                     for (int q = 0; q < SMAX; ++q) {
-                        if (pos_smp[q] >= 0) {
-                            double base = nom_s[pos_smp[q] * BT + bl];
+                        if (q < 5 || q < 4 + nother) {
+                            double base = nom_s[noff[q] + bl];
                             if (q < 4) base += dl[q];
                             acc = fma(fseg[q], base, acc);
                         }
@@ -354,13 +360,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                         double* cell = wfs + (size_t)lane * CS + 4 * bl;
                         const double4 dlt = *reinterpret_cast<const double4*>(cell);
                         const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
-                        double wf[4] = {0.0, 0.0, 0.0, 0.0};
+                        double wf[4];
 #pragma unroll
                         for (int q = 0; q < SMAX; ++q) {
-                            if (pos_smp[q] >= 0) {
-                                double base = nom_s[pos_smp[q] * BT + bl];
+                            if (q < 5 || q < 4 + nother) {
+                                double base = nom_s[noff[q] + bl];
                                 if (q < 4) base += dl[q];
-                                gacc[q] = fma(wgt[j], base, gacc[q]);
+                                gacc[q] = fma(wgt[j], base, gacc[q]);  // (never flushed for empty positions)
                                 if (q < 4) wf[q] = wgt[j] * fseg[q];
                             }
                         }
