@@ -350,7 +350,9 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     const bool valid = (tile * BT + bl < NB) && act[j];
                     const double n = nd_s[lane * (BT + 1) + bl];
                     if (valid) val += hf_pois_term(n, lam[j]);
-                    wgt[j] = valid ? (n / lam[j] - 1.0) : 0.0;
+                    // n * rcp(lambda) (correctly rounded reciprocal + one FMA) instead of the IEEE divide:
+                    // <= 1.5 ulp on n/lambda, same inf / NaN behaviour at lambda = 0
+                    wgt[j] = valid ? fma(n, __drcp_rn(lam[j]), -1.0) : 0.0;
                 }
                 if (GRAD) {
 #pragma unroll
