@@ -373,7 +373,7 @@ def run_b200(args):
         "roofline": roofline,
     }
 
-    if not args.no_toys:
+    if not args.no_toys and world == 1:  # single-GPU extra; the other ranks have left by now
         try:
             line["toy_fits"] = toy_fit_metric(batched)
         except Exception as exc:  # the headline metric must survive a failure of the extra one
