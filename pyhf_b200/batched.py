@@ -205,6 +205,27 @@ class DevicePlan:
                 _ptr(status), _ptr(niter), _stream()))
         return FitResult(x, fun, status, niter)
 
+    def fit_multistart(self, data, starts, lo=None, hi=None, fixed=None, **fit_kw):
+        """Every data row fitted from each of the K start points ``starts`` [K, P] in ONE lock-step
+        batch (K * N fits sharing the N data rows); per row the lowest converged minimum wins.
+
+        HistFactory likelihoods can be multimodal -- the reference's own validation model
+        2bin_2channel_coupledhistosys (tests/test_validation.py:620-690) has two basins in the
+        coupled histosys parameter, and SLSQP and a Newton method started at suggested_init end in
+        different ones.  No counterpart in the reference (a fit there has one start)."""
+        dev = self.device
+        data = _dev_tensor(data, dev)
+        if data.dim() == 1:
+            data = data.reshape(1, -1)
+        starts = _dev_tensor(starts, dev).reshape(-1, self.P)
+        N, K = data.shape[0], starts.shape[0]
+        rows = torch.arange(N, dtype=torch.int32, device=dev).repeat(K)
+        res = self.fit(data, starts.repeat_interleave(N, dim=0), lo, hi, fixed, data_map=rows, **fit_kw)
+        fun = torch.where(res.status == 0, res.fun, torch.full_like(res.fun, float("inf"))).reshape(K, N)
+        best = torch.argmin(fun, dim=0)                       # [N] winning start per row
+        pick = best.to(torch.int64) * N + torch.arange(N, device=dev)
+        return FitResult(res.x[pick], res.fun[pick], res.status[pick], res.niter[pick])
+
     # ------------------------------------------------------------------ curvature
     def hessian(self, pars, data, lo=None, hi=None, fixed=None):
         """Hessian of 2*NLL at pars [B, P] (or [P]) by central differences of the analytic
