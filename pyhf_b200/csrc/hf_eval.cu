@@ -48,7 +48,18 @@ __global__ void hf_transpose_pars_kernel(DevPlan pl, Work w, const double* __res
     }
 }
 
-constexpr int PREP_PPT = 4;  // points per thread: one coefficient fetch serves 4 evaluations
+// points per thread of hf_prep_kernel.  4 amortises one coefficient fetch over 4 evaluations, but
+// the block then walks 512 points x 99 normsys parameter rows = 400 KB, past L1, and every
+// parameter load becomes an L2 round trip (ncu: 14.5 long-scoreboard stalls per issue, fp64 pipe
+// 29 %); with 1 the rows of a block (99 KB) stay in L1: 1.25 -> 0.87 ms on C4.
+#ifndef HF_PREP_PPT
+#define HF_PREP_PPT 1
+#endif
+#ifndef HF_PREP_TB
+#define HF_PREP_TB 128
+#endif
+constexpr int PREP_TB = HF_PREP_TB;    // threads per block
+constexpr int PREP_PPT = HF_PREP_PPT;  // points per thread: one coefficient fetch serves 4 evaluations
 
 constexpr int PREP_CAP = 256;  // entries staged per pass
 constexpr int FIN_CAP = 96;
@@ -476,6 +487,10 @@ hf_finish_value_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* 
 }
 
 constexpr int FIN_PPT = 2;  // points per thread in hf_finish_grad_kernel
+#ifndef HF_FIN_UNROLL
+#define HF_FIN_UNROLL 1
+#endif
+constexpr int FIN_UNROLL = HF_FIN_UNROLL;  // entries of a parameter evaluated side by side
 
 __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                                       const double* __restrict__ data, int per_point,
@@ -538,6 +553,7 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                     q_w[i] = pl.sfp_q[kc + i];
                 }
                 __syncwarp();
+#pragma unroll FIN_UNROLL
                 for (int k = 0; k < ne; ++k) {
                     const int kind = kind_w[k];
                     const int q = q_w[k];
@@ -736,8 +752,8 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
     {
         const int items = pl.H + pl.S * pl.NSEG;
         int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
-        dim3 grid((unsigned)((ld + 128 * PREP_PPT - 1) / (128 * PREP_PPT)), (unsigned)gy);
-        hf_prep_kernel<<<grid, 128, (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, do_grad ? 1 : 0);
+        dim3 grid((unsigned)((ld + PREP_TB * PREP_PPT - 1) / (PREP_TB * PREP_PPT)), (unsigned)gy);
+        hf_prep_kernel<<<grid, PREP_TB, (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, do_grad ? 1 : 0);
         plan->launches++;
     }
     // accumulators: GsegT | gradT | mainv are carved back to back (hf_ensure_work): one memset
@@ -821,7 +837,7 @@ int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out
     hf_transpose_pars_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, pars, B, ld);
     const int items = pl.H + pl.S * pl.NSEG;
     int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
-    hf_prep_kernel<<<dim3((unsigned)((ld + 128 * PREP_PPT - 1) / (128 * PREP_PPT)), (unsigned)gy), 128,
+    hf_prep_kernel<<<dim3((unsigned)((ld + PREP_TB * PREP_PPT - 1) / (PREP_TB * PREP_PPT)), (unsigned)gy), PREP_TB,
                      (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, 0);
     const int64_t n = B * pl.D;
     hf_expected_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl, w, B, ld, out);
