@@ -60,6 +60,8 @@ SIGNATURES = {
                                C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
     "hf_fit_batch_mixed": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
                                      C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
+    "hf_fit_batch_masks": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _i64,
+                                     C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
     "hf_fit_batch_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64,
                                     C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
     "hf_hessian": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

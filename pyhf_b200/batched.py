@@ -150,13 +150,16 @@ class DevicePlan:
 
     # ------------------------------------------------------------------ fits
     def fit(self, data, init=None, lo=None, hi=None, fixed=None, max_iter=None, tol_edm=None,
-            tol_step=None, verbose=0, fixed_alt=None, use_alt=None, data_map=None):
+            tol_step=None, verbose=0, fixed_alt=None, use_alt=None, data_map=None, masks=None,
+            mask_id=None):
         """K3: N independent bounded fits of 2*NLL.  data [N, D] or [D]; init [N, P] or [P]
         (fixed parameters keep their init value).
 
         Mixed batches (hf_fit_batch_mixed): ``data_map`` [N] int32 picks the data row of each fit
         (data may then have any number of rows); fits with ``use_alt`` [N] != 0 use the mask
-        ``fixed_alt`` [P] instead of ``fixed``."""
+        ``fixed_alt`` [P] instead of ``fixed``.  ``masks`` [n_masks, P] with ``mask_id`` [N]
+        (hf_fit_batch_masks) is the general form: fit i uses row mask_id[i]; it replaces
+        ``fixed`` / ``fixed_alt`` / ``use_alt``."""
         dev = self.device
         data = _dev_tensor(data, dev)
         if data.dim() == 1:
@@ -172,6 +175,19 @@ class DevicePlan:
             N = data_map.numel()
         else:
             N = max(data.shape[0], init.shape[0])
+        if (masks is None) != (mask_id is None):
+            raise ValueError("masks and mask_id go together")
+        if masks is not None:
+            if fixed_alt is not None or use_alt is not None:
+                raise ValueError("a mask table replaces fixed_alt / use_alt")
+            masks = _dev_tensor(masks, dev, torch.uint8).reshape(-1, self.P).contiguous()
+            mask_id = _dev_tensor(mask_id, dev, torch.uint8).reshape(-1)
+            if not 1 <= masks.shape[0] <= 256:
+                raise ValueError("the mask table holds 1..256 rows")
+            if data_map is None:
+                N = max(N, mask_id.numel())
+            if mask_id.numel() != N or (N and int(mask_id.max()) >= masks.shape[0]):
+                raise ValueError("bad mask_id: one id < n_masks per fit")
         if (fixed_alt is None) != (use_alt is None):
             raise ValueError("fixed_alt and use_alt go together")
         if fixed_alt is not None:
@@ -196,6 +212,14 @@ class DevicePlan:
         fun = torch.empty(N, dtype=F64, device=dev)
         status = torch.empty(N, dtype=torch.int32, device=dev)
         niter = torch.empty(N, dtype=torch.int32, device=dev)
+        if masks is not None:
+            with torch.cuda.device(dev):
+                _lib.check(self._lib.hf_fit_batch_masks(
+                    self._h, _ptr(data), data.shape[0], None if data_map is None else _ptr(data_map),
+                    _ptr(init), init.shape[0], _ptr(lo), _ptr(hi), _ptr(masks), masks.shape[0],
+                    _ptr(mask_id), N, C.byref(opts), _ptr(x), _ptr(fun), _ptr(status), _ptr(niter),
+                    _stream()))
+            return FitResult(x, fun, status, niter)
         with torch.cuda.device(dev):
             _lib.check(self._lib.hf_fit_batch_mixed(
                 self._h, _ptr(data), data.shape[0], None if data_map is None else _ptr(data_map),
@@ -521,6 +545,36 @@ def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=
                 n_failed=int((qq["fixed"].status != 0).sum() + (qq["free"].status != 0).sum()))
 
 
+def asymptotic_pvalues(qmu, qmuA, test_stat="qtilde", calc_base_dist="normal"):
+    """Closing arithmetic of AsymptoticCalculator on tensors of any shape: test statistic
+    (calculators.py:416-445), observed p-values and the expected band (:447-523).  Plain torch
+    elementwise code on a handful of numbers per hypothesis.  Returns ``teststat``, ``CLsb``,
+    ``CLb``, ``CLs_obs`` (shape of qmu) and ``CLs_exp`` (one more trailing axis of 5:
+    n_sigma = 2, 1, 0, -1, -2 as in the reference)."""
+    sq, sqA = torch.sqrt(qmu), torch.sqrt(qmuA)
+    if test_stat in ("q", "q0"):
+        ts = sq - sqA
+    else:
+        safe = torch.where(sqA == 0, torch.ones_like(sqA), sqA)
+        ts = torch.where((sq <= sqA) | (sqA == 0), sq - sqA, (qmu - qmuA) / (2.0 * safe))
+    ndtr = torch.special.ndtr
+    cutoff = -sqA if calc_base_dist == "clipped_normal" else torch.full_like(sqA, float("-inf"))
+    nan = torch.full_like(sqA, float("nan"))
+
+    def pvalues(t):
+        clsb = torch.where(t >= cutoff, ndtr(-(t + sqA)), nan)     # sb_dist.shift = -sqrt(qmuA)
+        clb = torch.where(t >= cutoff, ndtr(-t), nan)
+        return clsb, clb, clsb / clb
+
+    clsb, clb, cls = pvalues(ts)
+    exp = []
+    for nsig in (2.0, 1.0, 0.0, -1.0, -2.0):
+        t = torch.full_like(sqA, nsig)
+        t = torch.where(t > cutoff, t, cutoff)                      # b_dist.expected_value
+        exp.append(pvalues(t)[2])
+    return dict(teststat=ts, CLsb=clsb, CLb=clb, CLs_obs=cls, CLs_exp=torch.stack(exp, dim=-1))
+
+
 def asymptotic_scan(plan: DevicePlan, mus, data, init=None, lo=None, hi=None, fixed=None,
                     test_stat="qtilde", calc_base_dist="normal", **fit_kw):
     """Asymptotic CLs for a whole scan of POI values in TWO batched fit launches.
@@ -583,29 +637,10 @@ def asymptotic_scan(plan: DevicePlan, mus, data, init=None, lo=None, hi=None, fi
     # their minimum and qmu_A = 0 identically; the two numerical minima differ by rounding
     # (~1e-12), which the square root below would turn into 1e-6 on CLs
     qmuA = torch.where(mus == asimov_mu, torch.zeros_like(qmuA), qmuA)
-    sq, sqA = torch.sqrt(qmu), torch.sqrt(qmuA)
-    if test_stat in ("q", "q0"):
-        ts = sq - sqA
-    else:
-        safe = torch.where(sqA == 0, torch.ones_like(sqA), sqA)
-        ts = torch.where((sq <= sqA) | (sqA == 0), sq - sqA, (qmu - qmuA) / (2.0 * safe))
-    ndtr = torch.special.ndtr
-    cutoff = -sqA if calc_base_dist == "clipped_normal" else torch.full_like(sqA, float("-inf"))
-    nan = torch.full_like(sqA, float("nan"))
-
-    def pvalues(t):
-        clsb = torch.where(t >= cutoff, ndtr(-(t + sqA)), nan)     # sb_dist.shift = -sqrt(qmuA)
-        clb = torch.where(t >= cutoff, ndtr(-t), nan)
-        return clsb, clb, clsb / clb
-
-    clsb, clb, cls = pvalues(ts)
-    exp = []
-    for nsig in (2.0, 1.0, 0.0, -1.0, -2.0):
-        t = torch.full_like(sqA, nsig)
-        t = torch.where(t > cutoff, t, cutoff)                      # b_dist.expected_value
-        exp.append(pvalues(t)[2])
+    pv = asymptotic_pvalues(qmu, qmuA, test_stat, calc_base_dist)
+    ts, clsb, clb, cls, cls_exp = pv["teststat"], pv["CLsb"], pv["CLb"], pv["CLs_obs"], pv["CLs_exp"]
     status = torch.cat([r1.status, r2.status])
-    return dict(mu=mus, CLs_obs=cls, CLs_exp=torch.stack(exp, dim=1), CLsb=clsb, CLb=clb, qmu=qmu,
+    return dict(mu=mus, CLs_obs=cls, CLs_exp=cls_exp, CLsb=clsb, CLb=clb, qmu=qmu,
                 qmuA=qmuA, teststat=ts, muhat=r1.x[0, poi], asimov_data=asimov.reshape(-1),
                 fits_data=r1, fits_asimov=r2, n_fits=2 * M + 3, n_failed=int((status != 0).sum()))
 

@@ -311,4 +311,5 @@ def compile_spec(spec, poi_name="mu", modifier_settings=None, clip_sample_data=N
         sf_coef=np.array(sf_coef, float).reshape(n_sf, 8), bf_par=bf_par,
         g_par=g_par, g_aux=g_aux, g_sigma=g_sigma, p_par=p_par, p_aux=p_aux, p_factor=p_factor,
         init=init, lo=bounds[:, 0], hi=bounds[:, 1], fixed=fixed, auxdata=np.asarray(auxdata, float),
+        par_slices={n: (par_start[n], ps["n"]) for n, ps in parsets.items()},
     )

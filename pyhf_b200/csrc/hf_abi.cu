@@ -23,7 +23,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                   int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
                   int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
                   int32_t* niter, cudaStream_t st, const uint8_t* fixed_alt = nullptr,
-                  const uint8_t* use_alt = nullptr, const int32_t* data_map = nullptr);
+                  const uint8_t* use_alt = nullptr, const int32_t* data_map = nullptr, int n_alt = 1);
 int hf_sample_toys_launch(hf_plan* plan, const double* pars, uint64_t seed, uint64_t offset,
                           int64_t N, double* out, cudaStream_t st);
 
@@ -471,6 +471,27 @@ int hf_fit_batch_mixed(hf_plan* plan, const double* data, int64_t data_rows, con
     }
     return hf_fit_launch(plan, data, data_rows, init, init_rows, lo, hi, fixed, N, opts, x, fun,
                          status, niter, (cudaStream_t)stream, fixed_alt, use_alt, data_map);
+}
+
+int hf_fit_batch_masks(hf_plan* plan, const double* data, int64_t data_rows, const int32_t* data_map,
+                       const double* init, int64_t init_rows, const double* lo, const double* hi,
+                       const uint8_t* masks, int32_t n_masks, const uint8_t* mask_id, int64_t N,
+                       const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
+                       int32_t* niter, void* stream) {
+    if (!plan || !data || !init || !lo || !hi || !masks || !x || !fun || !status) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    if (n_masks < 1 || n_masks > 256 || (n_masks > 1 && !mask_id)) {
+        hf_set_error("hf_fit_batch_masks: 1..256 masks, and mask_id when there is more than one");
+        return HF_ERR_INVALID;
+    }
+    if (n_masks == 1)
+        return hf_fit_launch(plan, data, data_rows, init, init_rows, lo, hi, masks, N, opts, x, fun,
+                             status, niter, (cudaStream_t)stream, nullptr, nullptr, data_map);
+    return hf_fit_launch(plan, data, data_rows, init, init_rows, lo, hi, masks, N, opts, x, fun,
+                         status, niter, (cudaStream_t)stream, masks + plan->P, mask_id, data_map,
+                         n_masks - 1);
 }
 
 int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,

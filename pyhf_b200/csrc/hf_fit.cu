@@ -51,8 +51,8 @@ struct FitDev {
     const int* pcol;     // [P]      FD column index of a global free parameter, else -1
     const double *lo, *hi;
     const uint8_t* fixed;         // [P] mask of the batch
-    const uint8_t* fixed_alt;     // [P] second mask (fits with use_alt set), or null
-    const uint8_t* use_alt;       // [N] per fit (global fit index), or null
+    const uint8_t* fixed_alt;     // [n_alt][P] further masks (fit i uses row use_alt[i] - 1), or null
+    const uint8_t* use_alt;       // [N] per fit (global fit index): 0 = `fixed`, k > 0 = row k - 1 of fixed_alt; or null
     const uint8_t* fixed_struct;  // [P] fixed under every mask of the batch (no FD column)
     const int* data_map;          // [N] data row of each fit (global fit index), or null
     int64_t toy0, data_rows;      // first fit of the current chunk; rows of the data array
@@ -67,7 +67,8 @@ __device__ __forceinline__ double fd_step(double x) { return kFdStep * fmax(1.0,
 
 // mask / data row of chunk-local fit `toy`
 __device__ __forceinline__ const uint8_t* fit_mask(const FitDev& s, int64_t toy) {
-    return (s.use_alt && s.use_alt[s.toy0 + toy]) ? s.fixed_alt : s.fixed;
+    const int k = s.use_alt ? (int)s.use_alt[s.toy0 + toy] : 0;
+    return k ? s.fixed_alt + (int64_t)(k - 1) * s.P : s.fixed;
 }
 __device__ __forceinline__ int64_t fit_data_row(const FitDev& s, int64_t toy) {
     if (s.data_map) return (int64_t)s.data_map[s.toy0 + toy];
@@ -837,8 +838,12 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                   int64_t init_rows, const double* lo, const double* hi, const uint8_t* fixed,
                   int64_t N, const hf_fit_opts* opts_in, double* x_out, double* fun_out,
                   int32_t* status_out, int32_t* niter_out, cudaStream_t st,
-                  const uint8_t* fixed_alt, const uint8_t* use_alt, const int32_t* data_map) {
+                  const uint8_t* fixed_alt, const uint8_t* use_alt, const int32_t* data_map, int n_alt) {
     if (N <= 0) return HF_OK;
+    if (n_alt < 1 || n_alt > 255) {
+        hf_set_error("the mask table holds 1..255 alternative masks (got %d)", n_alt);
+        return HF_ERR_INVALID;
+    }
     if ((!data_map && data_rows != 1 && data_rows != N) || data_rows < 1 ||
         (init_rows != 1 && init_rows != N)) {
         hf_set_error("data_rows/init_rows must be 1 or N (data_rows is free when a data map is given)");
@@ -856,11 +861,16 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
 
     // ---- column structure for this fixed mask (host: P is small)
     // (a parameter gets no FD column only when it is fixed under every mask of the batch)
-    std::vector<uint8_t> h_fixed(P), h_alt(P, 1);
+    std::vector<uint8_t> h_fixed(P), h_alt;
     HF_CUDA_OK(cudaMemcpyAsync(h_fixed.data(), fixed, P, cudaMemcpyDeviceToHost, st));
-    if (fixed_alt) HF_CUDA_OK(cudaMemcpyAsync(h_alt.data(), fixed_alt, P, cudaMemcpyDeviceToHost, st));
+    if (fixed_alt) {
+        h_alt.resize((size_t)n_alt * P);
+        HF_CUDA_OK(cudaMemcpyAsync(h_alt.data(), fixed_alt, (size_t)n_alt * P, cudaMemcpyDeviceToHost, st));
+    }
     HF_CUDA_OK(cudaStreamSynchronize(st));
-    for (int p = 0; p < P; ++p) h_fixed[p] = (h_fixed[p] && h_alt[p]) ? 1 : 0;
+    if (fixed_alt)
+        for (int k = 0; k < n_alt; ++k)
+            for (int p = 0; p < P; ++p) h_fixed[p] = (h_fixed[p] && h_alt[(size_t)k * P + p]) ? 1 : 0;
     std::vector<int32_t> colpar, pcolor(P), pcol(P, -1);
     std::vector<char> color_used(std::max(plan->fd_ncolors, 1), 0);
     for (int p = 0; p < P; ++p) {
