@@ -16,8 +16,13 @@ def __getattr__(name):
     # device-side API is imported lazily so that ``import pyhf_b200`` works on a CPU-only box
     if name in ("DevicePlan", "plan_for", "qmu_tilde_batch", "toy_hypotest", "FitResult",
                 "teststat", "pvalue_counts", "fp64_peak_tflops", "asymptotic_scan",
-                "upper_limit_from_scan", "empirical_expected_pvalues", "empirical_expected_value"):
+                "upper_limit_from_scan", "empirical_expected_pvalues", "empirical_expected_value",
+                "asymptotic_pvalues"):
         from . import batched
 
         return getattr(batched, name)
+    if name in ("patchset_hypotest", "apply_patch", "build_signal_group"):
+        from . import patchset
+
+        return getattr(patchset, name)
     raise AttributeError(name)

@@ -36,7 +36,8 @@ from .batched import DevicePlan
 from .compile import compile_spec
 from .plan import PlanError
 
-__all__ = ["apply_patch", "NotBatchable", "SignalGroup", "build_signal_group", "patchset_hypotest"]
+__all__ = ["apply_patch", "NotBatchable", "SignalGroup", "split_signal", "build_signal_group",
+           "group_masks", "patchset_hypotest"]
 
 
 class PatchError(ValueError):
@@ -178,67 +179,79 @@ class SignalGroup:
         self.spec, self.poi_names, self.users = spec, poi_names, users
 
 
+def split_signal(spec, poi, k=0):
+    """One patched model spec -> (background signature, variants): the samples without the POI
+    normfactor, as a canonical JSON string together with the channel list and the parameter
+    configuration (patches with equal signatures can share a group), and per channel the samples
+    that carry the POI, renamed for slot ``k`` of a group.  Raises :class:`NotBatchable`."""
+    import json
+
+    bkg, variants, names = [], {}, {}
+    for ch in spec["channels"]:
+        variants[ch["name"]] = []
+        for s in ch["samples"]:
+            if not _has_poi(s, poi):
+                bkg.append((ch["name"], s["name"], s))
+                continue
+            v = copy.deepcopy(s)
+            v["name"] = f"{s['name']}__p{k}"
+            for m in v["modifiers"]:
+                if m["type"] in ("staterror", "shapesys", "shapefactor"):
+                    raise NotBatchable(f"signal sample {s['name']!r} carries a {m['type']} "
+                                       "(per-patch constraint widths / parameter layout)")
+                if m["type"] == "normfactor" and m["name"] == poi:
+                    m["name"] = f"{poi}__p{k}"
+                else:
+                    names[m["name"]] = True
+            variants[ch["name"]].append(v)
+    if not any(variants.values()):
+        raise NotBatchable(f"no sample carries the POI normfactor {poi!r}")
+    bkg.sort(key=lambda t: (t[0], t[1]))
+    sig = json.dumps([[c["name"] for c in spec["channels"]], bkg, spec.get("parameters", [])], sort_keys=True)
+    return sig, variants, list(names)
+
+
 def build_signal_group(specs, poi):
     """Combine the patched model specs ``specs`` (``{"channels", "parameters"}`` each, all built
     from one background workspace) into one group model, or raise :class:`NotBatchable`."""
     K = len(specs)
     if K == 0:
         raise ValueError("no patches")
-    ref_pars = specs[0].get("parameters", [])
-    chan_names = [c["name"] for c in specs[0]["channels"]]
-    bkg, users = None, {}
-    group_channels = {c: [] for c in chan_names}
+    users, sig0 = {}, None
+    group_channels = {c["name"]: [] for c in specs[0]["channels"]}
     for k, sp in enumerate(specs):
-        if sp.get("parameters", []) != ref_pars:
-            raise NotBatchable(f"patch {k} edits the measurement's parameter configuration")
-        if [c["name"] for c in sp["channels"]] != chan_names:
-            raise NotBatchable(f"patch {k} adds, removes or reorders channels")
-        this_bkg = {}
-        n_var = 0
-        for ch in sp["channels"]:
-            for s in ch["samples"]:
-                if not _has_poi(s, poi):
-                    this_bkg[(ch["name"], s["name"])] = s
-                    continue
-                n_var += 1
-                v = copy.deepcopy(s)
-                v["name"] = f"{s['name']}__p{k}"
-                for m in v["modifiers"]:
-                    if m["type"] in ("staterror", "shapesys", "shapefactor"):
-                        raise NotBatchable(
-                            f"patch {k}: signal sample {s['name']!r} carries a {m['type']} "
-                            "(per-patch constraint widths / parameter layout)")
-                    if m["type"] == "normfactor" and m["name"] == poi:
-                        m["name"] = f"{poi}__p{k}"
-                    else:
-                        u = users.setdefault(m["name"], set())
-                        if u != "bkg":
-                            u.add(k)
-                group_channels[ch["name"]].append(v)
-        if n_var == 0:
-            raise NotBatchable(f"patch {k} leaves no sample with the POI normfactor {poi!r}")
-        if bkg is None:
-            bkg = this_bkg
-        elif this_bkg != bkg:
-            raise NotBatchable(f"patch {k} edits the background samples")
-    for (c, _), s in bkg.items():
-        for m in s["modifiers"]:
-            users[m["name"]] = "bkg"
+        try:
+            sig, variants, names = split_signal(sp, poi, k)
+        except NotBatchable as exc:
+            raise NotBatchable(f"patch {k}: {exc}") from None
+        if sig0 is None:
+            sig0 = sig
+        elif sig != sig0:
+            raise NotBatchable(f"patch {k} edits the background samples, the channels or the "
+                               "measurement's parameter configuration")
+        for c, lst in variants.items():
+            group_channels[c] += lst
+        for n in names:
+            users.setdefault(n, set()).add(k)
     channels = []
     for ch in specs[0]["channels"]:
-        c = ch["name"]
         out = {key: val for key, val in ch.items() if key != "samples"}
-        out["samples"] = [s for (cc, _), s in bkg.items() if cc == c] + group_channels[c]
+        keep = [s for s in ch["samples"] if not _has_poi(s, poi)]
+        for s in keep:
+            for m in s["modifiers"]:
+                users[m["name"]] = "bkg"
+        out["samples"] = keep + group_channels[ch["name"]]
         channels.append(out)
+    ref_pars = specs[0].get("parameters", [])
     poi_names = [f"{poi}__p{k}" for k in range(K)]
     pars = [p for p in ref_pars if p["name"] != poi]
-    poi_cfg = [p for p in ref_pars if p["name"] == poi]
-    for n in poi_names:
-        for p in poi_cfg:
-            q = copy.deepcopy(p)
-            q["name"] = n
-            pars.append(q)
-        users[n] = {int(n.rsplit("__p", 1)[1])}
+    for k, n in enumerate(poi_names):
+        for p in ref_pars:
+            if p["name"] == poi:
+                q = copy.deepcopy(p)
+                q["name"] = n
+                pars.append(q)
+        users[n] = {k}
     return SignalGroup({"channels": channels, "parameters": pars}, poi_names, users)
 
 
@@ -353,16 +366,22 @@ def patchset_hypotest(workspace, patches, mus=1.0, test_stat="qtilde", calc_base
         raise ValueError("no patches")
     results, mode = [None] * K, ["single"] * K
     todo = list(range(K))
-    if len(set(pois)) == 1 and test_stat in ("qtilde", "q"):
-        data_main = [_observed(w, s) for w, s in zip(patched, specs)]
-        for g0 in range(0, K, group_size):
-            idx = list(range(g0, min(K, g0 + group_size)))
-            if any(not np.array_equal(data_main[i], data_main[idx[0]]) for i in idx):
-                continue
+    # patches that can share a group: same background signature and the same observations
+    buckets = {}
+    for i in range(K):
+        try:
+            sig = split_signal(specs[i], pois[i])[0]
+        except NotBatchable:
+            continue
+        main = _observed(patched[i], specs[i])
+        buckets.setdefault((pois[i], sig, main.tobytes()), []).append(i)
+    for (poi, _, _), members in buckets.items():
+        for g0 in range(0, len(members), group_size):
+            idx = members[g0:g0 + group_size]
             try:
-                group = build_signal_group([specs[i] for i in idx], pois[0])
-                res = _group_hypotest(group, data_main[idx[0]], mus_t, test_stat, calc_base_dist,
-                                      device, modifier_settings, fit_kw)
+                group = build_signal_group([specs[i] for i in idx], poi)
+                res = _group_hypotest(group, _observed(patched[idx[0]], specs[idx[0]]), mus_t, test_stat,
+                                      calc_base_dist, device, modifier_settings, fit_kw)
             except (NotBatchable, PlanError):
                 continue
             for j, i in enumerate(idx):

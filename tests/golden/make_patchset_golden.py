@@ -3,12 +3,14 @@
 
     python tests/golden/make_patchset_golden.py      (needs baseline/_ref, see oracle/make_ref.py)
 
-Writes tests/golden/patchset.json with two cases:
+Writes tests/golden/patchset.json with three cases:
 
 * ``synthetic``: a 2-channel background workspace (histosys, normsys, lumi, staterror, shapesys on
   the backgrounds) and 6 signal patches (``add`` of a signal sample per channel: POI normfactor,
   a signal-only normsys shared by all patches, the background's JES histosys and lumi; one patch
   carries a normsys of its own, one adds no control-region sample);
+* ``synthetic_single``: two patches on the same workspace that must run one at a time (signal
+  with a staterror; patch that also edits a background systematic);
 * ``reference_example``: the reference's own tests/test_patchset/example_bkgonly.json +
   example_patchset.json (the patch *replaces* values inside the sample that carries the POI).
 
@@ -97,6 +99,22 @@ def synthetic_case():
     return ws, patches, [0.5, 1.0, 2.0]
 
 
+def single_case():
+    """two patches on the synthetic workspace that cannot join a group: the signal carries the
+    channel's staterror (its constraint width then depends on the patch); the patch also edits a
+    background systematic"""
+    ws, patches, _ = synthetic_case()
+    a = json.loads(json.dumps(patches[1]))
+    a["metadata"] = {"name": "sig_staterror", "values": [1000]}
+    a["patch"][0]["value"]["modifiers"].append(
+        {"name": "staterror_SR", "type": "staterror", "data": [0.9, 1.1, 0.8, 1.0]})
+    b = json.loads(json.dumps(patches[2]))
+    b["metadata"] = {"name": "sig_edits_bkg", "values": [1001]}
+    # patches[2] appends the signal ("-"), so the backgrounds keep their positions
+    b["patch"].append({"op": "replace", "path": "/channels/0/samples/0/modifiers/0/data/hi", "value": 1.12})
+    return ws, [a, b], [1.0, 2.0]
+
+
 def reference_example():
     d = "/root/reference/tests/test_patchset"
     ws = json.load(open(os.path.join(d, "example_bkgonly.json")))
@@ -137,7 +155,8 @@ def digest(ws, patches):
 
 def main():
     cases = {}
-    for name, fn in (("synthetic", synthetic_case), ("reference_example", reference_example)):
+    for name, fn in (("synthetic", synthetic_case), ("synthetic_single", single_case),
+                     ("reference_example", reference_example)):
         ws, patches, mus = fn()
         ref = run_reference(ws, patches, mus)
         cases[name] = dict(workspace=ws, patches=patches, mus=mus, patched_channels_sha256=digest(ws, patches), **ref)
