@@ -62,7 +62,10 @@ constexpr int PREP_TB = HF_PREP_TB;    // threads per block
 constexpr int PREP_PPT = HF_PREP_PPT;  // points per thread: one coefficient fetch serves 4 evaluations
 
 constexpr int PREP_CAP = 256;  // entries staged per pass
-constexpr int FIN_CAP = 96;
+#ifndef HF_FIN_CAP
+#define HF_FIN_CAP 12
+#endif
+constexpr int FIN_CAP = HF_FIN_CAP;  // entries of a parameter staged per pass (per warp)
 
 __global__ void hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
     extern __shared__ __align__(16) double prep_smem[];
@@ -486,20 +489,26 @@ hf_finish_value_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* 
     }
 }
 
-constexpr int FIN_PPT = 2;  // points per thread in hf_finish_grad_kernel
+#ifndef HF_FIN_PPT
+#define HF_FIN_PPT 2
+#endif
+constexpr int FIN_PPT = HF_FIN_PPT;  // points per thread in hf_finish_grad_kernel
 #ifndef HF_FIN_UNROLL
-#define HF_FIN_UNROLL 1
+#define HF_FIN_UNROLL 2
 #endif
 constexpr int FIN_UNROLL = HF_FIN_UNROLL;  // entries of a parameter evaluated side by side
 
-__global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
+#ifndef HF_FIN_MINB
+#define HF_FIN_MINB 3
+#endif
+__global__ void __launch_bounds__(256, HF_FIN_MINB)
+hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                                       const double* __restrict__ data, int per_point,
                                       const int* __restrict__ row_idx, double* __restrict__ grad,
                                       int x_in_smem) {
     // 128 points x 32 parameters per block; every thread carries 4 points so that one fetch of an
     // entry's coefficients serves 4 evaluations; transposed through shared memory so that both
     // the batch-major reads and the row-major writes coalesce
-    __shared__ double tile[32][32 * FIN_PPT + 1];
     extern __shared__ __align__(16) double fin_smem[];
     // per-warp staging of one parameter's entry table: [8 warps][max_sf_par] x (8 coef, kind, q)
     const int cap = min(max(pl.max_sf_par, 1), FIN_CAP);
@@ -525,7 +534,12 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
         }
         __syncthreads();
     }
-    for (int j = ty; j < 32; j += 8) {
+    // the warp's four parameters keep their sums in registers until every warp is done with xs:
+    // the transposition tile then reuses that shared memory (more resident blocks per SM)
+    double gout[4][FIN_PPT];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = ty + 8 * jj;
         const int p = p0 + j;
         double g[FIN_PPT], th[FIN_PPT];
         int64_t pt[FIN_PPT];
@@ -560,16 +574,25 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                     double cf[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) cf[c] = cf_w[8 * k + c];
+                    // one (warp-uniform) branch on the kind around ALL points of the thread, so
+                    // that their dependent Horner / reciprocal chains interleave
+                    double dl[FIN_PPT];
+                    if (kind == HF_SF_CODE4) {
+#pragma unroll
+                        for (int i = 0; i < FIN_PPT; ++i) dl[i] = hf_sf_dlog_code4(cf, th[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < FIN_PPT; ++i) dl[i] = (th[i] > 0.0) ? cf[0] : -cf[1];
+                    }
                     if (x_in_smem) {
 #pragma unroll
                         for (int i = 0; i < FIN_PPT; ++i)
-                            g[i] = fma(hf_sf_dlog(kind, cf, th[i]), xs[(size_t)q * NPB + tx + 32 * i], g[i]);
+                            g[i] = fma(dl[i], xs[(size_t)q * NPB + tx + 32 * i], g[i]);
                     } else {
                         const int64_t qrow = (int64_t)q * ld;
 #pragma unroll
                         for (int i = 0; i < FIN_PPT; ++i)
-                            g[i] = fma(hf_sf_dlog(kind, cf, th[i]),
-                                       w.FsegT[qrow + pt[i]] * w.GsegT[qrow + pt[i]], g[i]);
+                            g[i] = fma(dl[i], w.FsegT[qrow + pt[i]] * w.GsegT[qrow + pt[i]], g[i]);
                     }
                 }
                 }
@@ -613,8 +636,14 @@ __global__ void hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
             }
         }
 #pragma unroll
-        for (int i = 0; i < FIN_PPT; ++i) tile[j][tx + 32 * i] = g[i];
+        for (int i = 0; i < FIN_PPT; ++i) gout[jj][i] = g[i];
     }
+    __syncthreads();
+    double (*tile)[NPB + 1] = reinterpret_cast<double (*)[NPB + 1]>(xs);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int i = 0; i < FIN_PPT; ++i) tile[ty + 8 * jj][tx + 32 * i] = gout[jj][i];
     __syncthreads();
     for (int r = ty; r < 32 * FIN_PPT; r += 8) {
         const int64_t pt = pt0 + r;
@@ -808,8 +837,9 @@ finish:
         dim3 grid((unsigned)((B + 32 * FIN_PPT - 1) / (32 * FIN_PPT)), (unsigned)((pl.P + 31) / 32));
         size_t fin_smem = (size_t)std::min(std::max(pl.max_sf_par, 1), FIN_CAP) * (8 * 72) + 16;
         const size_t xs_bytes = sizeof(double) * (size_t)pl.S * pl.NSEG * 32 * FIN_PPT;
+        const size_t tile_bytes = sizeof(double) * 32 * (32 * FIN_PPT + 1);  // reuses the xs region
         const int x_in_smem = (fin_smem + xs_bytes <= 150 * 1024) ? 1 : 0;
-        if (x_in_smem) fin_smem += xs_bytes;
+        fin_smem += std::max(x_in_smem ? xs_bytes : (size_t)0, tile_bytes);
         HF_CUDA_OK(cudaFuncSetAttribute(hf_finish_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
         hf_finish_grad_kernel<<<grid, dim3(32, 8), fin_smem, st>>>(pl, w, B, ld, data, per_point, row_idx, grad, x_in_smem);
         plan->launches++;

@@ -157,22 +157,48 @@ __device__ __forceinline__ void hf_sf_accum(int kind, const double* __restrict__
     }
 }
 
-// dlog f / dtheta of a normsys entry (kind != THETA), branch-free
-__device__ __forceinline__ double hf_sf_dlog(int kind, const double* __restrict__ cf, double t) {
-    const double lnu = cf[0], lnd = cf[1];
-    if (kind == HF_SF_CODE4) {
-        double poly = cf[7], dpoly = 0.0;
+// reciprocal of a positive normal number: MUFU.RCP64H seed + the refinement steps of the IEEE
+// sequence, without its special-case slow path (a CALL inside the hot loop) -- full precision to
+// the last ulp or two, which is what a gradient term needs
+__device__ __forceinline__ double hf_rcp_pos(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// p ? a : b as ONE select instruction.  Written in PTX because the compiler otherwise turns a
+// ternary whose arms are expensive into a branch, and lanes are parameter points: ~15 % of the
+// alphas lie outside (-1, 1), so nearly every warp would run both arms one after the other.
+__device__ __forceinline__ double hf_selp(bool p, double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tselp.f64 %0, %1, %2, q;\n\t}"
+        : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+    return r;
+}
+
+// dlog f / dtheta of a code4 normsys entry, branch-free (interpolators/code4.py:178-239)
+__device__ __forceinline__ double hf_sf_dlog_code4(const double* __restrict__ cf, double t) {
+    double poly = cf[7], dpoly = 0.0;
 #pragma unroll
-        for (int i = 6; i >= 2; --i) {
-            dpoly = fma(dpoly, t, poly);
-            poly = fma(poly, t, cf[i]);
-        }
+    for (int i = 6; i >= 2; --i) {
         dpoly = fma(dpoly, t, poly);
-        poly = fma(poly, t, 1.0);
-        const double in = dpoly * __drcp_rn(poly);
-        return (t >= 1.0) ? lnu : ((t <= -1.0) ? -lnd : in);
+        poly = fma(poly, t, cf[i]);
     }
-    return (t > 0.0) ? lnu : -lnd;
+    dpoly = fma(dpoly, t, poly);
+    poly = fma(poly, t, 1.0);
+    const double in = dpoly * hf_rcp_pos(poly);
+    const double out = hf_selp(t >= 1.0, cf[0], -cf[1]);
+    return hf_selp((t > -1.0) && (t < 1.0), in, out);
+}
+
+// dlog f / dtheta of a normsys entry (kind != THETA)
+__device__ __forceinline__ double hf_sf_dlog(int kind, const double* __restrict__ cf, double t) {
+    if (kind == HF_SF_CODE4) return hf_sf_dlog_code4(cf, t);  // kind is uniform across the warp
+    return (t > 0.0) ? cf[0] : -cf[1];
 }
 
 // main / constraint Poisson term without the theta-independent lgamma(n+1):
