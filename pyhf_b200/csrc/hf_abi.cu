@@ -181,6 +181,27 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     const size_t o_ppar = pk.add(d->p_par, sizeof(int32_t) * d->n_pois);
     const size_t o_paux = pk.add(d->p_aux, sizeof(int32_t) * d->n_pois);
     const size_t o_pfac = pk.add(d->p_factor, sizeof(double) * d->n_pois);
+    // groups of up to 4 consecutive (sample, segment) products whose entry lists name the same
+    // parameters with the same kinds in the same order (normally: the samples of a channel share
+    // their normalisation systematics): hf_prep_kernel loads a parameter once per group
+    std::vector<int32_t> qg_first, qg_n;
+    for (int q = 0; q < S * NSEG;) {
+        int n = 1;
+        const int e0 = d->sf_ptr[q], len = d->sf_ptr[q + 1] - e0;
+        while (n < 4 && q + n < S * NSEG && len > 0) {
+            const int f0 = d->sf_ptr[q + n];
+            bool same = (d->sf_ptr[q + n + 1] - f0) == len;
+            for (int i = 0; same && i < len; ++i)
+                same = d->sf_par[e0 + i] == d->sf_par[f0 + i] && d->sf_kind[e0 + i] == d->sf_kind[f0 + i];
+            if (!same) break;
+            ++n;
+        }
+        qg_first.push_back(q);
+        qg_n.push_back(n);
+        q += n;
+    }
+    const size_t o_qgf = pk.add(qg_first.data(), sizeof(int32_t) * qg_first.size());
+    const size_t o_qgn = pk.add(qg_n.data(), sizeof(int32_t) * qg_n.size());
     const size_t o_ck = pk.add(cons_kind.data(), sizeof(int32_t) * P);
     const size_t o_ci = pk.add(cons_idx.data(), sizeof(int32_t) * P);
     pk.add(nullptr, 256);
@@ -210,6 +231,7 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     dp.bf_par = DP(int, o_bf); dp.g_par = DP(int, o_gpar); dp.g_aux = DP(int, o_gaux);
     dp.g_sigma = DP(double, o_gsig); dp.p_par = DP(int, o_ppar); dp.p_aux = DP(int, o_paux);
     dp.p_factor = DP(double, o_pfac); dp.par_cons_kind = DP(int, o_ck); dp.par_cons_idx = DP(int, o_ci);
+    dp.qg_first = DP(int, o_qgf); dp.qg_n = DP(int, o_qgn); dp.n_qg = (int)qg_first.size();
     dp.max_sf_q = 0; dp.max_sf_par = 0;
     for (int q = 0; q < S * NSEG; ++q) dp.max_sf_q = std::max(dp.max_sf_q, d->sf_ptr[q + 1] - d->sf_ptr[q]);
     for (int pp = 0; pp < P; ++pp) dp.max_sf_par = std::max(dp.max_sf_par, sfp_ptr[pp + 1] - sfp_ptr[pp]);

@@ -52,39 +52,133 @@ __global__ void hf_transpose_pars_kernel(DevPlan pl, Work w, const double* __res
 // the block then walks 512 points x 99 normsys parameter rows = 400 KB, past L1, and every
 // parameter load becomes an L2 round trip (ncu: 14.5 long-scoreboard stalls per issue, fp64 pipe
 // 29 %); with 1 the rows of a block (99 KB) stay in L1: 1.25 -> 0.87 ms on C4.
-#ifndef HF_PREP_PPT
-#define HF_PREP_PPT 1
-#endif
 #ifndef HF_PREP_TB
 #define HF_PREP_TB 128
 #endif
 constexpr int PREP_TB = HF_PREP_TB;    // threads per block
-constexpr int PREP_PPT = HF_PREP_PPT;  // points per thread: one coefficient fetch serves 4 evaluations
 
-constexpr int PREP_CAP = 256;  // entries staged per pass
 #ifndef HF_FIN_CAP
 #define HF_FIN_CAP 12
 #endif
 constexpr int FIN_CAP = HF_FIN_CAP;  // entries of a parameter staged per pass (per warp)
 
-__global__ void hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
+// F_q of NQ consecutive (sample, segment) products with identical (parameter, kind) lists: the
+// parameter value, its range predicates and the clamped log-domain argument are fetched /
+// computed once per entry and serve all NQ polynomials.  Everything per lane is select-based
+// (lanes are parameter points: a branch on alpha would diverge in nearly every warp); the
+// outside-range factors exp(+-alpha ln hi/lo) are summed in the log domain, one exp() per product.
+template <int NQ, int PPT>
+__device__ __forceinline__ void hf_prep_group(const DevPlan& pl, const Work& w, int64_t ld, int q0,
+                                              const int64_t* pt, const bool* ok, double* __restrict__ cf_s,
+                                              int* __restrict__ kind_s, int* __restrict__ par_s, int cap) {
+    double prod[NQ][PPT], logsum[NQ][PPT];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j)
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) { prod[j][i] = 1.0; logsum[j][i] = 0.0; }
+    const int len = pl.sf_ptr[q0 + 1] - pl.sf_ptr[q0];
+    // the entry tables go through shared memory: the coefficient stream (0.5 MB on C4) does not
+    // survive in L1 next to the parameter rows.  A uniform 16-byte shared load still costs two
+    // wavefronts, so the 64 bytes of an entry are the L1 cost of the kernel: every fetched
+    // coefficient serves PPT points.
+    for (int c0 = 0; c0 < len; c0 += cap) {
+        const int ne = min(cap, len - c0);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            const double* src = pl.sf_coef + 8 * ((int64_t)pl.sf_ptr[q0 + j] + c0);
+            for (int i = threadIdx.x; i < ne * 8; i += blockDim.x) cf_s[(size_t)j * cap * 8 + i] = src[i];
+        }
+        for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+            kind_s[i] = pl.sf_kind[pl.sf_ptr[q0] + c0 + i];
+            par_s[i] = pl.sf_par[pl.sf_ptr[q0] + c0 + i];
+        }
+        __syncthreads();
+        for (int e = 0; e < ne; ++e) {
+            const int kind = kind_s[e];  // uniform across the block
+            const int64_t prow = (int64_t)par_s[e] * ld;
+            double t[PPT];
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) t[i] = w.parsT[prow + pt[i]];
+            if (kind == HF_SF_THETA) {
+#pragma unroll
+                for (int j = 0; j < NQ; ++j)
+#pragma unroll
+                    for (int i = 0; i < PPT; ++i) prod[j][i] *= t[i];
+            } else if (kind == HF_SF_CODE4) {
+                bool inside[PPT], up[PPT];
+                double tm[PPT];
+#pragma unroll
+                for (int i = 0; i < PPT; ++i) {
+                    inside[i] = (t[i] > -1.0) && (t[i] < 1.0);
+                    up[i] = t[i] >= 1.0;
+                    tm[i] = hf_selp(inside[i], 0.0, t[i]);
+                }
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    double cf[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) cf[c] = cf_s[((size_t)j * cap + e) * 8 + c];
+                    const double nlnd = -cf[1];
+#pragma unroll
+                    for (int i = 0; i < PPT; ++i) {
+                        double poly = cf[7];
+#pragma unroll
+                        for (int c = 6; c >= 2; --c) poly = fma(poly, t[i], cf[c]);
+                        poly = fma(poly, t[i], 1.0);
+                        prod[j][i] *= hf_selp(inside[i], poly, 1.0);
+                        logsum[j][i] = fma(tm[i], hf_selp(up[i], cf[0], nlnd), logsum[j][i]);
+                    }
+                }
+            } else {  // code1: exp(alpha ln hi) above zero, exp(-alpha ln lo) below
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    const double lnu = cf_s[((size_t)j * cap + e) * 8], nlnd = -cf_s[((size_t)j * cap + e) * 8 + 1];
+#pragma unroll
+                    for (int i = 0; i < PPT; ++i)
+                        logsum[j][i] = fma(t[i], hf_selp(t[i] > 0.0, lnu, nlnd), logsum[j][i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NQ; ++j)
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            if (!ok[i]) continue;
+            double v = prod[j][i];
+            if (logsum[j][i] != 0.0) v *= exp(logsum[j][i]);
+            w.FsegT[(int64_t)(q0 + j) * ld + pt[i]] = v;
+        }
+}
+
+#ifndef HF_PREP_PPT
+#define HF_PREP_PPT 2
+#endif
+#ifndef HF_PREP_CHUNK
+#define HF_PREP_CHUNK 64
+#endif
+constexpr int PREP_PPT = HF_PREP_PPT;      // points per thread
+constexpr int PREP_CHUNK = HF_PREP_CHUNK;  // entries of a product staged per pass (x up to 4 products)
+
+__global__ void __launch_bounds__(PREP_TB)
+hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
     extern __shared__ __align__(16) double prep_smem[];
-    const int cap = min(max(pl.max_sf_q, 1), PREP_CAP);
-    double* cf_s = prep_smem;                                   // [cap][8]
-    int* kind_s = reinterpret_cast<int*>(cf_s + 8 * (size_t)cap);   // [cap]
-    int* par_s = kind_s + cap;                                  // [cap]
-    const int64_t base = (int64_t)blockIdx.x * blockDim.x * PREP_PPT + threadIdx.x;
+    const int cap = min(max(pl.max_sf_q, 1), PREP_CHUNK);
+    double* cf_s = prep_smem;                                       // [4][cap][8]
+    int* kind_s = reinterpret_cast<int*>(cf_s + 4 * 8 * (size_t)cap);   // [cap]
+    int* par_s = kind_s + cap;                                      // [cap]
     int64_t pt[PREP_PPT];
     bool ok[PREP_PPT];
 #pragma unroll
     for (int i = 0; i < PREP_PPT; ++i) {
-        pt[i] = base + (int64_t)i * blockDim.x;
+        pt[i] = ((int64_t)blockIdx.x * PREP_PPT + i) * blockDim.x + threadIdx.x;
         ok[i] = pt[i] < ld;
         if (!ok[i]) pt[i] = ld - 1;
     }
-    // blockIdx.y strides over the work items: first H histosys modifiers, then S*NSEG products
-    const int nq = pl.S * pl.NSEG;
-    for (int item = blockIdx.y; item < pl.H + nq; item += gridDim.y) {
+    // blockIdx.y strides over the work items: first H histosys modifiers, then the groups of
+    // (sample, segment) products
+    for (int item = blockIdx.y; item < pl.H + pl.n_qg; item += gridDim.y) {
         if (item < pl.H) {
             const int h = item;
 #pragma unroll
@@ -101,39 +195,13 @@ __global__ void hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
                 }
             }
         } else {
-            const int q = item - pl.H;
-            double prod[PREP_PPT], logsum[PREP_PPT];
-#pragma unroll
-            for (int i = 0; i < PREP_PPT; ++i) { prod[i] = 1.0; logsum[i] = 0.0; }
-            // the entry table of this (sample, segment) goes through shared memory: the
-            // coefficient stream (0.5 MB on C4) does not survive in L1 next to the parameter rows
-            for (int e0 = pl.sf_ptr[q]; e0 < pl.sf_ptr[q + 1]; e0 += cap) {
-            const int ne = min(cap, pl.sf_ptr[q + 1] - e0);
-            __syncthreads();
-            for (int i = threadIdx.x; i < ne * 8; i += blockDim.x) cf_s[i] = pl.sf_coef[8 * (int64_t)e0 + i];
-            for (int i = threadIdx.x; i < ne; i += blockDim.x) {
-                kind_s[i] = pl.sf_kind[e0 + i];
-                par_s[i] = pl.sf_par[e0 + i];
-            }
-            __syncthreads();
-#pragma unroll 2
-            for (int e = 0; e < ne; ++e) {
-                const int kind = kind_s[e];
-                const int64_t prow = (int64_t)par_s[e] * ld;
-                double cf[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) cf[c] = cf_s[8 * e + c];
-#pragma unroll
-                for (int i = 0; i < PREP_PPT; ++i)
-                    hf_sf_accum(kind, cf, w.parsT[prow + pt[i]], prod[i], logsum[i]);
-            }
-            }
-#pragma unroll
-            for (int i = 0; i < PREP_PPT; ++i) {
-                if (!ok[i]) continue;
-                double v = prod[i];
-                if (logsum[i] != 0.0) v *= exp(logsum[i]);
-                w.FsegT[(int64_t)q * ld + pt[i]] = v;
+            const int g = item - pl.H;
+            const int q0 = pl.qg_first[g];
+            switch (pl.qg_n[g]) {  // uniform across the block
+                case 1: hf_prep_group<1, PREP_PPT>(pl, w, ld, q0, pt, ok, cf_s, kind_s, par_s, cap); break;
+                case 2: hf_prep_group<2, PREP_PPT>(pl, w, ld, q0, pt, ok, cf_s, kind_s, par_s, cap); break;
+                case 3: hf_prep_group<3, PREP_PPT>(pl, w, ld, q0, pt, ok, cf_s, kind_s, par_s, cap); break;
+                default: hf_prep_group<4, PREP_PPT>(pl, w, ld, q0, pt, ok, cf_s, kind_s, par_s, cap); break;
             }
         }
     }
@@ -696,6 +764,14 @@ __global__ void hf_expected_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
     out[idx] = lam;
 }
 
+static void hf_prep_launch(const DevPlan& pl, const Work& w, int64_t ld, int do_grad, cudaStream_t st) {
+    const int items = pl.H + pl.n_qg;
+    const int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
+    const dim3 grid((unsigned)((ld + PREP_TB * PREP_PPT - 1) / (PREP_TB * PREP_PPT)), (unsigned)gy);
+    const size_t smem = (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CHUNK) * (4 * 64 + 8) + 16;
+    hf_prep_kernel<<<grid, PREP_TB, smem, st>>>(pl, w, ld, do_grad);
+}
+
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
@@ -779,10 +855,7 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
         plan->launches++;
     }
     {
-        const int items = pl.H + pl.S * pl.NSEG;
-        int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
-        dim3 grid((unsigned)((ld + PREP_TB * PREP_PPT - 1) / (PREP_TB * PREP_PPT)), (unsigned)gy);
-        hf_prep_kernel<<<grid, PREP_TB, (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, do_grad ? 1 : 0);
+        hf_prep_launch(pl, w, ld, do_grad ? 1 : 0, st);
         plan->launches++;
     }
     // accumulators: GsegT | gradT | mainv are carved back to back (hf_ensure_work): one memset
@@ -865,10 +938,7 @@ int hf_expected_launch(hf_plan* plan, const double* pars, int64_t B, double* out
     Work& w = plan->w;
     dim3 grid((unsigned)(ld / 32), (unsigned)((pl.P + 31) / 32));
     hf_transpose_pars_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, pars, B, ld);
-    const int items = pl.H + pl.S * pl.NSEG;
-    int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
-    hf_prep_kernel<<<dim3((unsigned)((ld + PREP_TB * PREP_PPT - 1) / (PREP_TB * PREP_PPT)), (unsigned)gy), PREP_TB,
-                     (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CAP) * 72 + 16, st>>>(pl, w, ld, 0);
+    hf_prep_launch(pl, w, ld, 0, st);
     const int64_t n = B * pl.D;
     hf_expected_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl, w, B, ld, out);
     plan->launches += 3;

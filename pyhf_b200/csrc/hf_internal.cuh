@@ -42,6 +42,9 @@ struct DevPlan {
     const int* par_cons_kind;    // [P] 0 none, 1 gauss, 2 poisson
     const int* par_cons_idx;     // [P] index into g_* / p_*
     // ---- DMMA path (hf_eval_mma.cu): tables re-tiled for bulk copies into shared memory
+    const int* qg_first;         // [n_qg] first q of a group of consecutive (sample, segment) products
+    const int* qg_n;             // [n_qg] 1..4 members with identical (parameter, kind) entry lists
+    int n_qg;
     int max_sf_q, max_sf_par;    // longest scalar-factor entry list per (sample, segment) / per parameter
     int mma_ok;                  // plan fits the tensor-core kernel (0 < H, R <= 4, <= 2 other samples)
     int mma_ntiles;              // bin tiles of HF_MMA_BT bins
