@@ -77,23 +77,46 @@ def _walk(doc, toks):
     return doc
 
 
-def _add(doc, toks, value):
+def _shallow(x):
+    return dict(x) if isinstance(x, dict) else list(x) if isinstance(x, list) else x
+
+
+def _own_parent(root, toks):
+    """Parent container of ``toks`` inside ``root`` (itself already a fresh shallow copy), with
+    every container on the way replaced by a shallow copy of its own: an operation then edits
+    only copies, and everything off its path stays shared with the input document."""
+    cur = root
+    for t in toks[:-1]:
+        if isinstance(cur, list):
+            i = _index(t, len(cur), False)
+        elif isinstance(cur, dict):
+            if t not in cur:
+                raise PatchError(f"member {t!r} not found")
+            i = t
+        else:
+            raise PatchError(f"cannot descend into a scalar at {t!r}")
+        cur[i] = _shallow(cur[i])
+        cur = cur[i]
+    return cur
+
+
+def _add(root, toks, value):
     if not toks:
         return value
-    parent = _walk(doc, toks[:-1])
+    parent = _own_parent(root, toks)
     if isinstance(parent, list):
         parent.insert(_index(toks[-1], len(parent), True), value)
     elif isinstance(parent, dict):
         parent[toks[-1]] = value
     else:
         raise PatchError("add into a scalar")
-    return doc
+    return root
 
 
-def _remove(doc, toks):
+def _remove(root, toks):
     if not toks:
         raise PatchError("cannot remove the document root")
-    parent = _walk(doc, toks[:-1])
+    parent = _own_parent(root, toks)
     if isinstance(parent, list):
         return parent.pop(_index(toks[-1], len(parent), False))
     if isinstance(parent, dict):
@@ -104,11 +127,14 @@ def _remove(doc, toks):
 
 
 def apply_patch(doc, patch):
-    """Apply an RFC 6902 patch (list of operations) to a copy of ``doc`` and return the copy --
-    what ``jsonpatch.JsonPatch(patch).apply(doc)`` does at workspace.py:439-440."""
+    """Apply an RFC 6902 patch (list of operations) and return the patched document -- what
+    ``jsonpatch.JsonPatch(patch).apply(doc)`` does at workspace.py:439-440.  ``doc`` is never
+    modified; the result SHARES every subtree the patch does not touch with ``doc`` (copy on
+    write along the operation paths: a signal patch on a large background workspace costs the
+    size of the patch, not of the workspace), so treat both as read-only afterwards."""
     if isinstance(patch, dict) and "patch" in patch:  # a patchset entry {"metadata":…, "patch":[…]}
         patch = patch["patch"]
-    doc = copy.deepcopy(doc)
+    doc = _shallow(doc)
     for op in patch:
         kind = op.get("op")
         toks = _tokens(op["path"])
@@ -179,6 +205,9 @@ class SignalGroup:
         self.spec, self.poi_names, self.users = spec, poi_names, users
 
 
+_SIG_CACHE = {}
+
+
 def split_signal(spec, poi, k=0):
     """One patched model spec -> (background signature, variants): the samples without the POI
     normfactor, as a canonical JSON string together with the channel list and the parameter
@@ -207,8 +236,17 @@ def split_signal(spec, poi, k=0):
     if not any(variants.values()):
         raise NotBatchable(f"no sample carries the POI normfactor {poi!r}")
     bkg.sort(key=lambda t: (t[0], t[1]))
-    sig = json.dumps([[c["name"] for c in spec["channels"]], bkg, spec.get("parameters", [])], sort_keys=True)
-    return sig, variants, list(names)
+    # canonical JSON of the background, cached by object identity: apply_patch shares the untouched
+    # samples with the background workspace, so all patches of a patchset hit one cache entry
+    pars = spec.get("parameters", [])
+    key = (tuple(c["name"] for c in spec["channels"]), tuple((c, n, id(smp)) for c, n, smp in bkg), id(pars))
+    hit = _SIG_CACHE.get(key)
+    if hit is None:
+        if len(_SIG_CACHE) > 64:
+            _SIG_CACHE.clear()
+        sig = json.dumps([list(key[0]), bkg, pars], sort_keys=True)
+        _SIG_CACHE[key] = hit = (sig, [smp for _, _, smp in bkg], pars)  # keeps the ids alive
+    return hit[0], variants, list(names)
 
 
 def build_signal_group(specs, poi):

@@ -71,6 +71,27 @@ def test_apply_patch_errors(doc, patch):
         PS.apply_patch(doc, patch)
 
 
+def test_apply_patch_copies_only_along_the_operation_paths():
+    """the patched workspace shares every untouched subtree with the background workspace (a
+    signal patch costs the size of the patch), and the background is never modified"""
+    c = CASES["synthetic"]
+    ws = c["workspace"]
+    before = copy.deepcopy(ws)
+    out = PS.apply_patch(ws, c["patches"][1])          # inserts the signal at samples/0
+    assert ws == before
+    assert out["observations"] is ws["observations"] and out["measurements"] is ws["measurements"]
+    for ch_out, ch_in in zip(out["channels"], ws["channels"]):
+        assert ch_out is not ch_in and ch_out["samples"] is not ch_in["samples"]
+        assert [s["name"] for s in ch_out["samples"]] == ["signal", "ttbar", "wjets"]
+        assert ch_out["samples"][1] is ch_in["samples"][0] and ch_out["samples"][2] is ch_in["samples"][1]
+    # all patches of a patchset therefore share one background signature computation
+    sigs = {PS.split_signal(PS._model_spec(PS.apply_patch(ws, p), 0)[0], "mu")[0] for p in c["patches"]}
+    assert len(sigs) == 1
+    # ... and an equal but separately built background lands in the same bucket
+    other = PS.apply_patch(copy.deepcopy(ws), c["patches"][0])
+    assert PS.split_signal(PS._model_spec(other, 0)[0], "mu")[0] in sigs
+
+
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_patched_workspaces_match_the_golden_digest(case):
     c = CASES[case]
