@@ -2,7 +2,7 @@
 fit launch): a refresh costs n_global + 1 = 201 gradients on C4 against 21 on C3, so the optimum
 differs.  One process, plan built once without pyhf.
 
-    python tools/c4_refresh_sweep.py [ntoys] [ratio[:exact_below] ...]
+    python tools/c4_refresh_sweep.py [ntoys] [ratio[:exact_below] ...]   (SWEEP_MODEL=c3 for the C3 model)
 
 ``exact_below`` (HF_FIT_EXACT_BELOW): the exact Hessian replaces the Fisher matrix (Hessian on the
 Asimov data of the current point, positive semi-definite) once the estimated distance to the
@@ -21,15 +21,15 @@ from pyhf_b200.compile import compile_spec  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 ratios = sys.argv[2:] or ["0.05", "0.2", "0.4", "0.6", "0.8"]
-hp = compile_spec(synth.spec_c4(), poi_name="mu")
+hp = compile_spec(synth.spec_c3() if os.environ.get("SWEEP_MODEL") == "c3" else synth.spec_c4(), poi_name="mu")
 plan = batched.DevicePlan(hp)
 toys = plan.sample_toys(hp.init, n, seed=5)
 batched.qmu_tilde_batch(plan, 1.0, toys[:64])  # warm-up (workspace allocation)
 ref = None
 for r in ratios:
-    rr, _, eb = r.partition(":")
-    os.environ["HF_FIT_REFRESH"] = rr
-    os.environ["HF_FIT_EXACT_BELOW"] = eb or "10"
+    f = (r.split(":") + [""])[:2]
+    os.environ["HF_FIT_REFRESH"] = f[0]
+    os.environ["HF_FIT_EXACT_BELOW"] = f[1] or "10"
     torch.cuda.synchronize()
     t0 = time.time()
     out = batched.qmu_tilde_batch(plan, 1.0, toys)
