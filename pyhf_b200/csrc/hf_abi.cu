@@ -401,12 +401,15 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
     double* d_grad = grad_host ? d_out + B : nullptr;
     // Pipeline over chunks of points: H2D of chunk i+1, the kernels of chunk i and D2H of chunk
     // i-1 overlap (PCIe is full duplex); the copy streams are ordered against `st` by events.
-    // Chunk = 3 full waves of the dominant kernel (one CTA of HF_MMA_M points per SM and wave):
-    // a 16384-point chunk is 3.46 waves on 148 SMs and pays for 4.
+    // Chunks are whole waves of the dominant kernel (one CTA of HF_MMA_M points per SM and wave:
+    // a 16384-point chunk would be 3.46 waves on 148 SMs and pay for 4).  The first upload and the
+    // last download cannot overlap anything, so the schedule ramps 1, 2, 3, 3, ... waves and ends
+    // with a single wave.
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t CH = (int64_t)sms * HF_MMA_M * 3;
+    const int64_t WAVE = (int64_t)sms * HF_MMA_M;
+    const int64_t CH = WAVE * 3;
     if (B <= 2 * CH || data_rows != 1) {
         HF_CUDA_OK(cudaMemcpyAsync(d_pars, pars_host, sizeof(double) * n_pars, cudaMemcpyHostToDevice, st));
         HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * n_data, cudaMemcpyHostToDevice, st));
@@ -422,7 +425,17 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
         HF_CUDA_OK(cudaStreamCreateWithFlags(&plan->s_in, cudaStreamNonBlocking));
         HF_CUDA_OK(cudaStreamCreateWithFlags(&plan->s_out, cudaStreamNonBlocking));
     }
-    const int64_t nch = (B + CH - 1) / CH;
+    std::vector<int64_t> ch_b0, ch_nb;
+    {
+        int64_t b0 = 0, left = B - WAVE;  // the closing single wave is set aside
+        for (int k = 0; left > 0; ++k) {
+            const int64_t nb = std::min<int64_t>(left, WAVE * std::min(k + 1, 3));
+            ch_b0.push_back(b0); ch_nb.push_back(nb);
+            b0 += nb; left -= nb;
+        }
+        ch_b0.push_back(b0); ch_nb.push_back(B - b0);
+    }
+    const int64_t nch = (int64_t)ch_b0.size();
     std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);
     cudaEvent_t ev_start;
     HF_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
@@ -431,7 +444,7 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
     HF_CUDA_OK(cudaStreamWaitEvent(plan->s_out, ev_start, 0));
     HF_CUDA_OK(cudaMemcpyAsync(d_data, data_host, sizeof(double) * n_data, cudaMemcpyHostToDevice, plan->s_in));
     for (int64_t c = 0; c < nch; ++c) {
-        const int64_t b0 = c * CH, nb = std::min<int64_t>(CH, B - b0);
+        const int64_t b0 = ch_b0[c], nb = ch_nb[c];
         HF_CUDA_OK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
         HF_CUDA_OK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         HF_CUDA_OK(cudaMemcpyAsync(d_pars + b0 * P, pars_host + b0 * P, sizeof(double) * nb * P,
@@ -439,7 +452,7 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
         HF_CUDA_OK(cudaEventRecord(ev_in[c], plan->s_in));
     }
     for (int64_t c = 0; c < nch; ++c) {
-        const int64_t b0 = c * CH, nb = std::min<int64_t>(CH, B - b0);
+        const int64_t b0 = ch_b0[c], nb = ch_nb[c];
         HF_CUDA_OK(cudaStreamWaitEvent(st, ev_in[c], 0));
         rc = hf_eval_launch(plan, d_pars + b0 * P, d_data, 1, nb, d_out + b0, d_grad ? d_grad + b0 * P : nullptr, st);
         if (rc) return rc;

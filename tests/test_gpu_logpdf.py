@@ -171,6 +171,28 @@ def test_host_buffer_entry_point(golden, cuda):
     assert (np.abs(grad.numpy() - g["grad"]) / scale).max() < 1e-10
 
 
+@pytest.mark.parametrize("B", [28417, 40001])
+def test_host_buffer_entry_point_pipelined(B, golden, cuda):
+    """above two 3-wave chunks the host entry pipelines H2D / kernels / D2H over a ramped chunk
+    schedule (1, 2, 3, 3, ... waves and a closing single wave; ragged here): every point must come
+    back in its own slot, equal to the device-resident call"""
+    g = golden("mixed_code4p_code4")
+    hp = g.host_plan()
+    plan = _dev_plan(g, cuda)
+    rng = np.random.default_rng(11)
+    pars = hp.init + rng.normal(0, 0.3, (B, hp.n_pars)) * (1 - hp.fixed)
+    pars = torch.as_tensor(np.clip(pars, hp.lo + 1e-6, hp.hi)).pin_memory()
+    data = torch.as_tensor(g["data"]).reshape(1, -1).pin_memory()
+    out = torch.full((B,), np.nan, dtype=torch.float64).pin_memory()
+    grad = torch.full((B, hp.n_pars), np.nan, dtype=torch.float64).pin_memory()
+    plan.logpdf_grad_host(pars, data, out, grad)
+    v, gr = plan.logpdf_grad(pars.to(cuda), g["data"])
+    ok = torch.isfinite(v).cpu()
+    assert ok.float().mean() > 0.9 and torch.equal(ok, torch.isfinite(out))
+    np.testing.assert_allclose(out[ok].numpy(), v.cpu()[ok].numpy(), rtol=1e-13, atol=0)
+    np.testing.assert_allclose(grad[ok].numpy(), gr.cpu()[ok].numpy(), rtol=1e-12, atol=1e-12)
+
+
 @pytest.mark.parametrize("name", ["mixed_code4p_code4", "mixed_code0_code1", "val_2bin_histosys",
                                   "val_2bin_2channel_coupledhistosys"])
 @pytest.mark.parametrize("B", [256, 1000])
