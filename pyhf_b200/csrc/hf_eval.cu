@@ -626,15 +626,42 @@ hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
             // plain theta factor (finite at theta == 0: the POI sits on its bound in q~ fits)
             const int k0 = pl.sfp_ptr[p], e1 = pl.sfp_ptr[p + 1];
             if (k0 < e1 && pl.sfp_kind[k0] != HF_SF_THETA) {
+                // the chunk after the current one travels through registers while the current one
+                // is evaluated: its L2 latency (7 chunks per parameter on C4) is off the warp's
+                // critical path
+                constexpr int NPF = (FIN_CAP * 8 + 31) / 32, NPI = (FIN_CAP + 31) / 32;
+                double pf[NPF];
+                int pk[NPI], pq[NPI];
+                auto fetch = [&](int kc) {
+                    const int ne = min(cap, e1 - kc);
+#pragma unroll
+                    for (int r = 0; r < NPF; ++r) {
+                        const int i = tx + 32 * r;
+                        pf[r] = (i < ne * 8) ? pl.sfp_coef[8 * (int64_t)kc + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < NPI; ++r) {
+                        const int i = tx + 32 * r;
+                        pk[r] = (i < ne) ? pl.sfp_kind[kc + i] : 0;
+                        pq[r] = (i < ne) ? pl.sfp_q[kc + i] : 0;
+                    }
+                };
+                fetch(k0);
                 for (int kc = k0; kc < e1; kc += cap) {
                 const int ne = min(cap, e1 - kc);
                 __syncwarp();
-                for (int i = tx; i < ne * 8; i += 32) cf_w[i] = pl.sfp_coef[8 * (int64_t)kc + i];
-                for (int i = tx; i < ne; i += 32) {
-                    kind_w[i] = pl.sfp_kind[kc + i];
-                    q_w[i] = pl.sfp_q[kc + i];
+#pragma unroll
+                for (int r = 0; r < NPF; ++r) {
+                    const int i = tx + 32 * r;
+                    if (i < ne * 8) cf_w[i] = pf[r];
+                }
+#pragma unroll
+                for (int r = 0; r < NPI; ++r) {
+                    const int i = tx + 32 * r;
+                    if (i < ne) { kind_w[i] = pk[r]; q_w[i] = pq[r]; }
                 }
                 __syncwarp();
+                if (kc + cap < e1) fetch(kc + cap);
 #pragma unroll FIN_UNROLL
                 for (int k = 0; k < ne; ++k) {
                     const int kind = kind_w[k];
