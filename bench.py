@@ -22,6 +22,17 @@ Keys beyond the base contract:
 """
 import argparse
 import json
+
+
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+# banner from C when NCCL_DEBUG asks for it), so file descriptor 1 is pointed at stderr for the
+# whole run and the JSON line goes to a private copy of the original stdout.
+import os as _os  # noqa: E402
+import sys as _sys  # noqa: E402
+
+_sys.stdout.flush()
+_JSON_OUT = _os.fdopen(_os.dup(1), "w")
+_os.dup2(2, 1)
 import os
 import subprocess
 import sys
@@ -232,7 +243,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------- the CUDA arm
@@ -396,7 +407,7 @@ def run_b200(args):
         }
     if dist is not None:
         dist.destroy_process_group()
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def toy_fit_metric(batched, ntoys=100000):
