@@ -12,7 +12,8 @@ import os
 
 import torch
 
-__all__ = ["shard_range", "init_from_env", "all_gather_1d", "all_gather_cols", "toy_hypotest_distributed"]
+__all__ = ["shard_range", "init_from_env", "all_gather_1d", "all_gather_cols", "toy_hypotest_distributed",
+           "patchset_hypotest_distributed"]
 
 
 def shard_range(n, rank, world):
@@ -100,3 +101,55 @@ def toy_hypotest_distributed(plan, mu_test, data_obs, ntoys, seed=0, **kw):
     start, count = shard_range(ntoys, rank, world)
     return batched.toy_hypotest(plan, mu_test, data_obs, count, seed=seed, toy_offset=start,
                                 gather=lambda t: all_gather_cols(t, ntoys), **kw)
+
+
+_PATCH_FIELDS = ("CLs_obs", "CLs_exp", "CLsb", "CLb", "teststat", "qmu", "qmuA", "muhat")
+
+
+def patchset_hypotest_distributed(workspace, patches, mus=1.0, **kw):
+    """``patchset.patchset_hypotest`` with the signal patches sharded over the ranks of the default
+    process group by contiguous index (SURVEY.md section 8 rows e + f4: signal points are
+    independent units).  Every rank builds its own group models from its shard; ONE all-gather of
+    a ``[rows, n_patches]`` block returns every patch's results to every rank."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from . import patchset
+
+    if isinstance(patches, dict):
+        patches = patches["patches"]
+    patches = list(patches)
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, world = 0, 1
+    K = len(patches)
+    M = int(np.atleast_1d(np.asarray(mus, float)).size)
+    start, count = shard_range(K, rank, world)
+    if world == 1:
+        return patchset.patchset_hypotest(workspace, patches, mus, **kw)
+    widths = {"CLs_exp": 5 * M, "muhat": 1}
+    rows = sum(widths.get(f, M) for f in _PATCH_FIELDS) + 3
+    device = kw.get("device")
+    if count:
+        out = patchset.patchset_hypotest(workspace, patches[start:start + count], mus, **kw)
+        cols = [out[f].reshape(count, -1) for f in _PATCH_FIELDS]
+        extra = torch.tensor([[1.0 if m == "group" else 0.0, out["n_fits"] / count, out["n_failed"] / count]
+                              for m in out["mode"]], dtype=cols[0].dtype, device=cols[0].device)
+        block = torch.cat(cols + [extra], dim=1).T.contiguous()
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        block = torch.zeros(rows, 0, dtype=torch.float64, device=dev)
+    full = all_gather_cols(block, K).T  # [K, rows]
+    res, pos = {}, 0
+    for f in _PATCH_FIELDS:
+        wdt = widths.get(f, M)
+        res[f] = full[:, pos:pos + wdt]
+        pos += wdt
+    res["CLs_exp"] = res["CLs_exp"].reshape(K, M, 5)
+    res["muhat"] = res["muhat"].reshape(K)
+    res["mode"] = ["group" if v > 0.5 else "single" for v in full[:, pos].tolist()]
+    res["n_fits"] = int(round(float(full[:, pos + 1].sum())))
+    res["n_failed"] = int(round(float(full[:, pos + 2].sum())))
+    res["mu"] = torch.as_tensor(np.atleast_1d(np.asarray(mus, float)), device=full.device)
+    return res
