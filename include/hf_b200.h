@@ -160,7 +160,8 @@ int hf_fit_batch_mixed(hf_plan* plan, const double* data, int64_t data_rows, con
                        int64_t N, const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
                        int32_t* niter, void* stream);
 /* The same lock-step batch with a TABLE of masks: masks [n_masks][P] (1..256 rows), fit i uses row
- * mask_id[i] (every id must be < n_masks; NULL only when n_masks == 1).  A parameter gets a
+ * mask_id[i] (ids must be < n_masks -- larger ones are clamped to the last row; NULL only when
+ * n_masks == 1).  A parameter gets a
  * finite-difference Hessian column when it is free under at least one row.  This is what lets ONE
  * batch serve many signal hypotheses that share a background model (pyhf_b200/patchset.py: one
  * normfactor per signal point, all but one fixed at zero in every fit; reference workflow

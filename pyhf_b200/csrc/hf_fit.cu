@@ -53,6 +53,7 @@ struct FitDev {
     const uint8_t* fixed;         // [P] mask of the batch
     const uint8_t* fixed_alt;     // [n_alt][P] further masks (fit i uses row use_alt[i] - 1), or null
     const uint8_t* use_alt;       // [N] per fit (global fit index): 0 = `fixed`, k > 0 = row k - 1 of fixed_alt; or null
+    int n_alt;                    // rows of fixed_alt (ids beyond it are clamped, never read out of bounds)
     const uint8_t* fixed_struct;  // [P] fixed under every mask of the batch (no FD column)
     const int* data_map;          // [N] data row of each fit (global fit index), or null
     int64_t toy0, data_rows;      // first fit of the current chunk; rows of the data array
@@ -67,7 +68,7 @@ __device__ __forceinline__ double fd_step(double x) { return kFdStep * fmax(1.0,
 
 // mask / data row of chunk-local fit `toy`
 __device__ __forceinline__ const uint8_t* fit_mask(const FitDev& s, int64_t toy) {
-    const int k = s.use_alt ? (int)s.use_alt[s.toy0 + toy] : 0;
+    const int k = s.use_alt ? min((int)s.use_alt[s.toy0 + toy], s.n_alt) : 0;
     return k ? s.fixed_alt + (int64_t)(k - 1) * s.P : s.fixed;
 }
 __device__ __forceinline__ int64_t fit_data_row(const FitDev& s, int64_t toy) {
@@ -965,6 +966,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     s.colpar = d_colpar; s.pcolor = d_pcolor; s.partner = d_partner; s.pcol = d_pcol;
     s.lo = lo; s.hi = hi; s.fixed = fixed;
     s.fixed_alt = fixed_alt; s.use_alt = use_alt; s.fixed_struct = d_struct; s.data_map = data_map;
+    s.n_alt = fixed_alt ? n_alt : 0;
     s.data_rows = data_rows; s.toy0 = 0;
     HF_CUDA_OK(cudaMemcpyAsync(d_struct, h_fixed.data(), P, cudaMemcpyHostToDevice, st));
     s.chol_in_smem = chol_in_smem ? 1 : 0;
