@@ -161,11 +161,11 @@ int hf_fit_batch_mixed(hf_plan* plan, const double* data, int64_t data_rows, con
                        int32_t* niter, void* stream);
 /* The same lock-step batch with a TABLE of masks: masks [n_masks][P] (1..256 rows), fit i uses row
  * mask_id[i] (ids must be < n_masks -- larger ones are clamped to the last row; NULL only when
- * n_masks == 1).  A parameter gets a
- * finite-difference Hessian column when it is free under at least one row.  This is what lets ONE
- * batch serve many signal hypotheses that share a background model (pyhf_b200/patchset.py: one
- * normfactor per signal point, all but one fixed at zero in every fit; reference workflow
- * workspace.py:392-442 + patchset.py:300, one Model and five fits per patch). */
+ * n_masks == 1).  A parameter gets a finite-difference Hessian column when it is free under at
+ * least one row.  This is what lets ONE batch serve many signal hypotheses that share a background
+ * model (pyhf_b200/patchset.py: one normfactor per signal point, all but one fixed at zero in
+ * every fit; reference workflow workspace.py:392-442 + patchset.py:300, one Model and five fits
+ * per patch). */
 int hf_fit_batch_masks(hf_plan* plan, const double* data, int64_t data_rows, const int32_t* data_map,
                        const double* init, int64_t init_rows, const double* lo, const double* hi,
                        const uint8_t* masks, int32_t n_masks, const uint8_t* mask_id, int64_t N,
