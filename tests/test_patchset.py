@@ -233,3 +233,67 @@ def test_grouped_hypotest_bookkeeping_against_reference_cls(case, monkeypatch):
     assert out["n_fits"] == 2 * K * (M + 1) + 1 and out["n_failed"] == 0
     np.testing.assert_allclose(out["CLs_obs"].numpy(), np.array(c["cls_obs_tight"]), rtol=0, atol=1e-6)
     np.testing.assert_allclose(out["CLs_exp"].numpy(), np.array(c["cls_exp_tight"]), rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------ properties
+def _paths(doc, prefix=""):
+    """every JSON pointer into doc (containers and leaves), RFC 6901 escaped"""
+    out = [prefix]
+    if isinstance(doc, dict):
+        for k, v in doc.items():
+            out += _paths(v, prefix + "/" + k.replace("~", "~0").replace("/", "~1"))
+    elif isinstance(doc, list):
+        for i, v in enumerate(doc):
+            out += _paths(v, f"{prefix}/{i}")
+    return out
+
+
+def test_apply_patch_properties_on_random_documents():
+    """size-independent properties: add then remove (and move there and back) restores the
+    document, replace by the present value changes nothing, copy duplicates, the input is never
+    modified -- on random nested documents with keys that need pointer escaping"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    keys = st.sampled_from(["a", "b", "c/d", "e~f", "", "0", "-"])
+    leaves = st.one_of(st.integers(-5, 5), st.floats(allow_nan=False, allow_infinity=False), st.booleans(),
+                       st.none(), st.text(max_size=3))
+    docs = st.recursive(leaves, lambda ch: st.one_of(st.lists(ch, max_size=4), st.dictionaries(keys, ch, max_size=4)),
+                        max_leaves=25)
+    tops = st.one_of(st.lists(docs, max_size=4), st.dictionaries(keys, docs, min_size=1, max_size=4))
+
+    @settings(max_examples=150, deadline=None)
+    @given(tops, docs, st.data())
+    def check(doc, value, data):
+        before = copy.deepcopy(doc)
+        paths = [p for p in _paths(doc) if p]
+        if not paths:
+            return
+        path = data.draw(st.sampled_from(paths))
+        present = PS._walk(doc, PS._tokens(path))
+        # replace by the present value: nothing changes; the input is untouched
+        assert PS.apply_patch(doc, [{"op": "replace", "path": path, "value": present}]) == before
+        # test succeeds on the present value, fails on a different one
+        PS.apply_patch(doc, [{"op": "test", "path": path, "value": present}])
+        with pytest.raises(PS.PatchError):
+            PS.apply_patch(doc, [{"op": "test", "path": path, "value": ["certainly", "different", 1]}])
+        # remove then add back at the same pointer restores the document (list order included)
+        assert PS.apply_patch(doc, [{"op": "remove", "path": path},
+                                    {"op": "add", "path": path, "value": present}]) == before
+        # add next to it (lists: insert before; dicts: a new member), then remove again
+        parent_path, _, last = path.rpartition("/")
+        parent = PS._walk(doc, PS._tokens(parent_path))
+        new = parent_path + ("/" + last if isinstance(parent, list) else "/new~0member")
+        if isinstance(parent, list) or "new~member" not in parent:
+            out = PS.apply_patch(doc, [{"op": "add", "path": new, "value": value}])
+            assert PS._walk(out, PS._tokens(new)) == value
+            assert PS.apply_patch(out, [{"op": "remove", "path": new}]) == before
+            # copy duplicates the value, move there and back is the identity
+            dup = PS.apply_patch(doc, [{"op": "copy", "from": path, "path": new}])
+            assert PS._walk(dup, PS._tokens(new)) == present
+            if isinstance(parent, dict):
+                there = PS.apply_patch(doc, [{"op": "move", "from": path, "path": new}])
+                assert PS.apply_patch(there, [{"op": "move", "from": new, "path": path}]) == before
+        assert doc == before
+
+    check()
