@@ -57,3 +57,34 @@ def test_compiler_rejects_out_of_scope():
     spec["channels"][0]["samples"][0]["modifiers"].append({"name": "x", "type": "custom", "data": None})
     with pytest.raises(PlanError):
         compile_spec(spec)
+
+
+@pytest.mark.needs_pyhf
+@pytest.mark.parametrize("case", ["synthetic", "reference_example"])
+def test_compiler_matches_live_extraction_on_signal_group_models(case):
+    """the group model of SURVEY.md section 8 row f4 (background once, K signal variants with a
+    POI each; pyhf_b200/patchset.py) and every per-patch model: the tables compiled from the spec
+    equal what the reference's own model builder produces for it"""
+    import json
+    import os
+
+    import pyhf
+
+    from pyhf_b200 import patchset as PS
+    from pyhf_b200.plan import extract_plan
+
+    c = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "patchset.json")))[case]
+    patched = [PS.apply_patch(c["workspace"], p) for p in c["patches"]]
+    specs, pois = zip(*[PS._model_spec(w, 0) for w in patched])
+    group = PS.build_signal_group(list(specs), pois[0])
+    ref = extract_plan(pyhf.Model(group.spec, poi_name=group.poi_names[-1]))
+    mine = compile_spec(group.spec, poi_name=group.poi_names[-1])
+    _assert_same(mine.arrays(), ref.arrays())
+    # parameter bookkeeping the mask table is built from
+    model = pyhf.Model(group.spec, poi_name=group.poi_names[0])
+    for name, (start, n) in mine.par_slices.items():
+        sl = model.config.par_slice(name)
+        assert (sl.start, sl.stop - sl.start) == (start, n), name
+    for spec, poi in zip(specs, pois):
+        _assert_same(compile_spec(spec, poi_name=poi).arrays(),
+                     extract_plan(pyhf.Model(spec, poi_name=poi)).arrays())
