@@ -324,7 +324,7 @@ def _group_hypotest(group, data_main, mus, test_stat, calc_base_dist, device, mo
     host = compile_spec(group.spec, poi_name=None, modifier_settings=modifier_settings)
     plan = DevicePlan(host, device)
     dev = plan.device
-    K, M, P = len(group.poi_names), mus.numel(), host.n_pars
+    K, M = len(group.poi_names), mus.numel()
     masks, poi_idx, init0 = group_masks(group, host)
     poi_t = torch.as_tensor(poi_idx, device=dev)
     poi_init = torch.as_tensor(host.init[poi_idx], device=dev)
