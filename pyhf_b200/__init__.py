@@ -21,7 +21,7 @@ def __getattr__(name):
         from . import batched
 
         return getattr(batched, name)
-    if name in ("patchset_hypotest", "apply_patch", "build_signal_group"):
+    if name in ("patchset_hypotest", "patchset_upper_limits", "apply_patch", "build_signal_group"):
         from . import patchset
 
         return getattr(patchset, name)

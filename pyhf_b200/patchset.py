@@ -37,7 +37,7 @@ from .compile import compile_spec
 from .plan import PlanError
 
 __all__ = ["apply_patch", "NotBatchable", "SignalGroup", "split_signal", "build_signal_group",
-           "group_masks", "patchset_hypotest"]
+           "group_masks", "patchset_hypotest", "patchset_upper_limits"]
 
 
 class PatchError(ValueError):
@@ -441,4 +441,23 @@ def patchset_hypotest(workspace, patches, mus=1.0, test_stat="qtilde", calc_base
            for k in ("CLs_obs", "CLs_exp", "CLsb", "CLb", "teststat", "muhat", "qmu", "qmuA")}
     out.update(mu=mus_t, mode=mode, n_fits=int(round(sum(r["n_fits"] for r in results))),
                n_failed=int(round(sum(r["n_failed"] for r in results))))
+    return out
+
+
+def patchset_upper_limits(workspace, patches, scan, level=0.05, **kw):
+    """Observed and expected upper limits on the POI of every signal patch: the asymptotic CLs scan
+    of ``pyhf.infer.intervals.upper_limits.upper_limit(data, model, scan)`` (linear_grid_scan,
+    upper_limits.py:148-213: one ``hypotest`` per scan point, then ``np.interp(level, cls[::-1],
+    scan[::-1])``, :16-18) for all patches at once -- ``patchset_hypotest`` with ``mus = scan``.
+    Returns its dict plus ``obs_limit`` [K] and ``exp_limits`` [K, 5] (n_sigma = 2, 1, 0, -1, -2
+    ordering of ``CLs_exp``, as the reference returns them)."""
+    scan = np.asarray(scan, float).reshape(-1)
+    out = patchset_hypotest(workspace, patches, scan, **kw)
+    obs = out["CLs_obs"].detach().cpu().numpy()
+    exp = out["CLs_exp"].detach().cpu().numpy()
+    K = obs.shape[0]
+    out["obs_limit"] = torch.as_tensor([batched.upper_limit_from_scan(scan, obs[k], level) for k in range(K)],
+                                       device=out["CLs_obs"].device)
+    out["exp_limits"] = torch.as_tensor([batched.upper_limit_from_scan(scan, exp[k], level) for k in range(K)],
+                                        device=out["CLs_obs"].device)
     return out

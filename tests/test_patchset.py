@@ -297,3 +297,17 @@ def test_apply_patch_properties_on_random_documents():
         assert doc == before
 
     check()
+
+
+def test_upper_limits_per_patch_against_the_reference(monkeypatch):
+    """patchset_upper_limits = the reference's upper_limit(data, model, scan) for every patch
+    (tests/golden/add_patchset_limits.py), here through the oracle-backed stand-in for DevicePlan"""
+    c = CASES["synthetic"]
+    lim = c["limits"]
+    monkeypatch.setattr(PS, "DevicePlan", OraclePlan)
+    patches = [c["patches"][k] for k in lim["patches"]]
+    out = PS.patchset_upper_limits(c["workspace"], patches, lim["scan"], device="cpu")
+    assert out["mode"] == ["group", "group"] and out["n_failed"] == 0
+    np.testing.assert_allclose(out["obs_limit"].numpy(), lim["obs_limit_tight"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out["exp_limits"].numpy(), lim["exp_limits_tight"], rtol=0, atol=2e-6)
+    assert out["CLs_obs"][:, 0].tolist() == [1.0, 1.0]   # mu = 0: the degenerate point, no NaN
