@@ -398,7 +398,8 @@ hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restri
                     live = false;
                 }
                 term[i] = valid ? hf_pois_term(n, l) : 0.0;
-                wgt[i] = (valid && live) ? (n / l - 1.0) : 0.0;
+                // d/dl [xlogy(n, l) - l] is exactly -1 for n == 0 (also at l == 0, where n / l would be NaN)
+                wgt[i] = (valid && live) ? ((n == 0.0) ? -1.0 : n / l - 1.0) : 0.0;
             }
 #pragma unroll
             for (int i = 0; i < PT; ++i) {
@@ -725,7 +726,10 @@ hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                         const double sg = pl.g_sigma[ci];
                         g[i] += (data[row * pl.D + pl.NB + pl.g_aux[ci]] - th[i]) / (sg * sg);
                     } else {
-                        g[i] += data[row * pl.D + pl.NB + pl.p_aux[ci]] / th[i] - pl.p_factor[ci];
+                        {
+                            const double a = data[row * pl.D + pl.NB + pl.p_aux[ci]];
+                            g[i] += ((a == 0.0) ? 0.0 : a / th[i]) - pl.p_factor[ci];
+                        }
                     }
                 }
             }

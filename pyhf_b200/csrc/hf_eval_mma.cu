@@ -352,7 +352,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     if (valid) val += hf_pois_term(n, lam[j]);
                     // n * rcp(lambda) (correctly rounded reciprocal + one FMA) instead of the IEEE divide:
                     // <= 1.5 ulp on n/lambda, same inf / NaN behaviour at lambda = 0
-                    wgt[j] = valid ? fma(n, __drcp_rn(lam[j]), -1.0) : 0.0;
+                    // (n == 0: the derivative of xlogy(0, l) - l is exactly -1, also at l == 0)
+                    wgt[j] = valid ? ((n == 0.0) ? -1.0 : fma(n, __drcp_rn(lam[j]), -1.0)) : 0.0;
                 }
                 if (GRAD) {
 #pragma unroll
@@ -412,7 +413,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             const double n = nd_s[lane * (BT + 1) + bl];
             if (valid) val += hf_pois_term(n, lam);
             if (GRAD) {
-                const double wgt = valid ? (n / lam - 1.0) : 0.0;
+                const double wgt = valid ? ((n == 0.0) ? -1.0 : n / lam - 1.0) : 0.0;
                 double wf[4];
 #pragma unroll
                 for (int q = 0; q < SMAX; ++q) {

@@ -125,8 +125,23 @@ def eval_block(model, pars, data):
     pyhf.set_backend("numpy", "scipy")
     lp = np.array([float(model.logpdf(p, data)[0]) for p in pars])
     ed = np.array([np.asarray(model.expected_data(p)) for p in pars])
+    grad = autograd(model, pars, data)
+    # autograd through xlogy(0, 0) is NaN (rate exactly 0 under n = 0) although ln L is finite and
+    # one-sidedly differentiable there: such rows carry forward differences of the reference
+    # ln L (Richardson, h and h/2) and are flagged in grad_fd (compared to 1e-6, not 1e-12)
+    grad_fd = np.zeros(len(pars), bool)
+    for r in range(len(pars)):
+        if np.isfinite(lp[r]) and not np.all(np.isfinite(grad[r])):
+            f = lambda x: float(model.logpdf(x, data)[0])  # noqa: E731
+            for j in range(pars.shape[1]):
+                h = 1e-4 * max(1.0, abs(pars[r, j]))
+                e = np.zeros(pars.shape[1]); e[j] = h
+                d1 = (f(pars[r] + e) - lp[r]) / h
+                d2 = (f(pars[r] + 0.5 * e) - lp[r]) / (0.5 * h)
+                grad[r, j] = 2.0 * d2 - d1
+            grad_fd[r] = True
     return dict(pars=pars, data=np.asarray(data, float), logpdf=lp, expected_data=ed,
-                grad=autograd(model, pars, data))
+                grad=grad, grad_fd=grad_fd)
 
 
 def fit_block(model, data, mu_test, tight_tol=1e-12):
@@ -437,6 +452,100 @@ def stage_scan():
                                               settings={"modifier_settings": {"normsys": {"interpcode": "code1"}}})))
     np.savez_compressed(os.path.join(HERE, "scan_2bin_2channel.npz"), **d)
     print("obs UL", d["obs_limit"], d["obs_limit_tight"], "exp", d["exp_limits"], d["exp_limits_tight"])
+
+
+
+# ------------------------------------------------------------------ edge cases (round 2)
+def spec_clipping():
+    """the model of the reference's tests/test_pdf.py:1098-1165 (test_pdf_clipping): hi/lo histosys
+    templates that drive the expected rates negative at alpha = -0.6"""
+    hs = lambda n, hi, lo: {"data": {"hi_data": hi, "lo_data": lo}, "name": n, "type": "histosys"}  # noqa: E731
+    return {
+        "channels": [
+            {"name": "ch1", "samples": [{"name": "signal", "data": [100.0, 100.0], "modifiers": [
+                {"data": None, "name": "mu_sig", "type": "normfactor"},
+                hs("np_1", [125.0, 75.0], [175.0, 10.0]), hs("np_2", [125.0, 75.0], [175.0, 10.0])]}]},
+            {"name": "ch2", "samples": [{"name": "signal", "data": [15000.0], "modifiers": [
+                {"data": None, "name": "mu_sig", "type": "normfactor"},
+                hs("np_1", [15500.0], [1200.0]), hs("np_2", [15500.0], [1200.0])]}]},
+        ]
+    }
+
+
+def spec_empty_signal_bin():
+    """a signal-only bin with zero observed events: at mu = 0 (the background-only / Asimov fits of
+    every asymptotic CLs) its expected rate is exactly 0 with n = 0 -- xlogy(0, 0) = 0
+    (tensor/numpy_backend.py:435-436), and the analytic gradient must stay finite there"""
+    return {
+        "channels": [
+            {"name": "SR", "samples": [
+                {"name": "sig", "data": [4.0, 6.0, 3.0], "modifiers": [
+                    {"name": "mu", "type": "normfactor", "data": None}]},
+                {"name": "bkg", "data": [0.0, 55.0, 30.0], "modifiers": [
+                    {"name": "bnorm", "type": "normsys", "data": {"hi": 1.1, "lo": 0.9}},
+                    {"name": "bshape", "type": "shapesys", "data": [0.0, 5.0, 4.0]}]},
+            ]}
+        ]
+    }
+
+
+def stage_edge():
+    pyhf.set_backend("numpy", "scipy")
+    # ---- clipping: pdf.py:696-699 (by sample), :708-709 (by bin)
+    spec = spec_clipping()
+    data = [100.0, 100.0, 10.0, 0.0, 0.0]
+    for tag, kw in (("clip_sample0", {"clip_sample_data": 0.0}), ("clip_bin0", {"clip_bin_data": 0.0}),
+                    ("clip_both", {"clip_sample_data": 20.0, "clip_bin_data": 150.0})):
+        model = pyhf.Model(spec, poi_name="mu_sig", validate=False, **kw)
+        pars = par_batch(model, 8, 7)
+        names = model.config.par_names
+        pars[1] = [(-0.6 if "np" in n else 1.0) for n in names]   # the reference test's point
+        pars[2] = [(-1.4 if "np" in n else 0.7) for n in names]   # extrapolation branch, clipped too
+        pars[3] = [(0.3 if "np" in n else 1.2) for n in names]    # nothing clipped
+        blocks = eval_block(model, pars, data)
+        if tag != "clip_both":
+            assert np.allclose(blocks["expected_data"][1][:3], [1.830496e02, 0.0, 0.0], atol=1e-3)  # test_pdf.py:1187-1198
+        blocks.update(fit_block(model, data, 1.0))
+        save(tag, spec, model, blocks, dict(mu_test=1.0, poi_name="mu_sig", settings=kw))
+    # the all-modifier model with clips that bite on some cells only
+    for tag, kw in (("mixed_clip", {"clip_sample_data": 9.0, "clip_bin_data": 60.0}),):
+        spec, model = mixed_model(**kw)
+        np.random.seed(3)
+        data = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(model.config.suggested_init())).sample((1,))[0])
+        pars = par_batch(model, 8, 4)
+        for nm in ("jes", "jer", "sys_sig"):
+            sl = model.config.par_map[nm]["slice"]
+            pars[1, sl] = 1.7
+            pars[2, sl] = -2.3
+        pars[3, model.config.poi_index] = 0.2     # signal cells below the per-sample clip
+        blocks = eval_block(model, pars, data)
+        save(tag, spec, model, blocks, dict(mu_test=1.0, settings=kw, poi_name="mu"))
+    # ---- signal-only bin with zero observed events
+    spec = spec_empty_signal_bin()
+    model = pyhf.Model(spec, poi_name="mu", validate=False)
+    data = [0.0, 58.0, 37.0] + model.config.auxdata
+    pars = par_batch(model, 8, 8)
+    pars[1, model.config.poi_index] = 0.0        # lambda = 0 with n = 0: value finite, gradient finite
+    blocks = eval_block(model, pars, data)
+    assert np.all(np.isfinite(blocks["logpdf"]))
+    blocks.update(fit_block(model, data, 1.0))
+    for mu0 in (0.0,):   # the Asimov-generating fit of AsymptoticCalculator (calculators.py:45-97)
+        for tagt, kwt in (("default", {}), ("tight", {"tolerance": 1e-12})):
+            pyhf.set_backend("numpy", pyhf.optimize.scipy_optimizer(**kwt))
+            x0, f0 = pyhf.infer.mle.fixed_poi_fit(mu0, data, model, return_fitted_val=True)
+            blocks[f"fixed0_x_{tagt}"], blocks[f"fixed0_fun_{tagt}"] = np.asarray(x0), float(f0)
+    pyhf.set_backend("numpy", "scipy")
+    cb = cls_block(model, data, 1.0, "qtilde")
+    blocks.update(cb)
+    # data with n > 0 in the bin whose rate is 0 at mu = 0: ln L = -inf (tests/test_tensor.py:304-314)
+    d2 = [3.0, 58.0, 37.0] + model.config.auxdata
+    p0 = np.array(model.config.suggested_init(), float)
+    p0[model.config.poi_index] = 0.0
+    blocks["neg_inf_data"] = np.asarray(d2, float)
+    blocks["neg_inf_pars"] = p0
+    blocks["neg_inf_logpdf"] = float(model.logpdf(p0, d2)[0])
+    assert blocks["neg_inf_logpdf"] == -np.inf
+    save("empty_signal_bin", spec, model, blocks, dict(mu_test=1.0, poi_name="mu", test_stat="qtilde"))
 
 
 

@@ -8,7 +8,7 @@ from conftest import golden_names
 from pyhf_b200.compile import compile_spec
 from pyhf_b200.plan import PlanError
 
-WITH_PLAN = [n for n in golden_names() if n != "c4"]
+WITH_PLAN = [n for n in golden_names() if n not in ("c4", "c4_fits")]
 
 
 def _settings(g):
@@ -32,7 +32,9 @@ def _assert_same(a, b):
 @pytest.mark.parametrize("name", WITH_PLAN)
 def test_compiler_matches_golden_plan(golden, name):
     g = golden(name)
-    plan = compile_spec(g.spec(), poi_name=g.meta.get("poi_name", "mu"), modifier_settings=_settings(g))
+    s = g.meta.get("settings") or {}
+    clips = {k: s[k] for k in ("clip_sample_data", "clip_bin_data") if k in s}
+    plan = compile_spec(g.spec(), poi_name=g.meta.get("poi_name", "mu"), modifier_settings=_settings(g), **clips)
     _assert_same(plan.arrays(), g.plan_arrays())
 
 

@@ -3,11 +3,11 @@ reproduces the reference's scipy fits."""
 import numpy as np
 import pytest
 
-from conftest import SMALL
+from conftest import CLIPPED, FIT_GOLDENS
 from oracle import fit_proto as F
 
 
-@pytest.mark.parametrize("name", [n for n in SMALL if n != "val_2bin_2channel_coupledhistosys"])
+@pytest.mark.parametrize("name", [n for n in FIT_GOLDENS if n != "val_2bin_2channel_coupledhistosys" and n not in CLIPPED])
 def test_proto_matches_reference_fits(name, golden):
     g = golden(name)
     pl = g.oracle_plan()

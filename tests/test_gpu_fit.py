@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import SMALL
+from conftest import CLIPPED, FIT_GOLDENS
 
 pytestmark = pytest.mark.gpu
 
@@ -41,7 +41,7 @@ def _check_optimal(op, hp, x, data, fixed, tol=2e-5):
     assert np.abs(pg).max() < tol, (np.abs(pg).max(), np.argmax(np.abs(pg)))
 
 
-@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("name", FIT_GOLDENS)
 def test_single_fits_match_reference(name, golden, cuda):
     g = golden(name)
     hp, op = g.host_plan(), g.oracle_plan()
@@ -58,6 +58,12 @@ def test_single_fits_match_reference(name, golden, cuda):
     x_free, f_free = free.x[0].cpu().numpy(), float(free.fun[0])
     x_fix, f_fix = fix.x[0].cpu().numpy(), float(fix.fun[0])
     assert x_fix[hp.poi_index] == mu
+    if name in CLIPPED:
+        # kinked likelihood (rates clipped from below): first-order optimality is not defined on
+        # a kink; the bar is "never a worse minimum than either reference fit"
+        assert f_free <= min(float(g["free_fun_default"]), float(g["free_fun_tight"])) + 1e-6
+        assert f_fix <= min(float(g["fixed_fun_default"]), float(g["fixed_fun_tight"])) + 1e-6
+        return
     _check_optimal(op, hp, x_free, data, hp.fixed)
     _check_optimal(op, hp, x_fix, data, fixed_mask)
     # twice_nll of the returned point is what the reference's objective returns there

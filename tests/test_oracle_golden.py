@@ -7,7 +7,7 @@
 import numpy as np
 import pytest
 
-from conftest import SMALL
+from conftest import CLIPPED, FIT_GOLDENS, SMALL
 from oracle import hf_oracle as O
 
 
@@ -23,9 +23,12 @@ def test_oracle_logpdf_expected_grad(name, golden):
     assert np.allclose(v2, v, rtol=1e-15)
     hp = g.host_plan()
     err = np.abs(gr - g["grad"]) / (np.abs(g["grad"]).max(axis=1, keepdims=True) + 1e-300)
+    finite = np.isfinite(g["logpdf"])  # ln L = -inf (rates clipped to 0 under n > 0): no gradient to compare
     if hp.hs_code == 0 or (hp.sf_kind == 2).any():
-        err = err[1:]  # kink of code0/code1 at alpha == 0 (autograd picks abs'(0) = 0)
-    assert err.max() < 1e-12
+        finite[0] = False  # kink of code0/code1 at alpha == 0 (autograd picks abs'(0) = 0)
+    fd = g["grad_fd"] if "grad_fd" in g else np.zeros(len(finite), bool)  # rows pinned by finite differences
+    assert (finite & ~fd).sum() >= 3 and err[finite & ~fd].max() < 1e-12
+    assert not (finite & fd).any() or err[finite & fd].max() < 1e-6
 
 
 @pytest.mark.needs_pyhf
@@ -63,12 +66,16 @@ def test_known_answers_of_reference_tests(golden):
     HostPlan.from_arrays(g.plan_arrays())  # round trip
 
 
-@pytest.mark.parametrize("name", [n for n in SMALL if n != "val_2bin_2channel_coupledhistosys"])
+@pytest.mark.parametrize("name", [n for n in FIT_GOLDENS if n != "val_2bin_2channel_coupledhistosys"])
 def test_oracle_tight_fit_matches_reference_fits(name, golden):
     g = golden(name)
     pl = g.oracle_plan()
     x, f = O.fit(pl, g["data"])
     assert f <= float(g["free_fun_default"]) + 1e-6
+    if name in CLIPPED:  # kinked likelihood: never a worse minimum than the reference's
+        xf, ff = O.fit(pl, g["data"], fixed_vals=[(pl.poi_index, g.meta["mu_test"])])
+        assert f <= float(g["free_fun_tight"]) + 1e-6 and ff <= float(g["fixed_fun_tight"]) + 1e-6
+        return
     assert abs(f - float(g["free_fun_tight"])) < 1e-6
     xf, ff = O.fit(pl, g["data"], fixed_vals=[(pl.poi_index, g.meta["mu_test"])])
     assert abs(ff - float(g["fixed_fun_tight"])) < 1e-6
