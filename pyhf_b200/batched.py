@@ -473,7 +473,7 @@ def qmu_tilde_batch(plan: DevicePlan, mu, data, init=None, lo=None, hi=None, fix
 
 def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=0, init=None,
                  lo=None, hi=None, fixed=None, mode="qtilde", gather=None, profile=None,
-                 return_expected_set=False, **fit_kw):
+                 return_expected_set=False, max_failed_fraction=None, **fit_kw):
     """Toy-based CLs for one signal strength: the arithmetic of ToyCalculator.distributions /
     pvalues (reference infer/calculators.py:754-915) with every fit batched on the device: the
     4 * ntoys toy fits (2 hypotheses x {POI fixed, free}) are one lock-step batch.
@@ -482,7 +482,9 @@ def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=
     [toy_offset, toy_offset + ntoys) are this rank's shard.  ``profile`` (optional dict) receives
     the wall time of each phase (adds a device synchronisation per phase).
     ``return_expected_set``: also the (-2..2 sigma) band of CLsb / CLb / CLs over the
-    background-only toys (``expected``), the O(N log N) form of calculators.py:924-973."""
+    background-only toys (``expected``), the O(N log N) form of calculators.py:924-973.
+    Toys with a failed fit are excluded from the p-values and counted in ``n_failed`` (global over
+    all ranks); ``max_failed_fraction`` turns more than that fraction into an error."""
     import time
 
     dev = plan.device
@@ -526,23 +528,32 @@ def toy_hypotest(plan: DevicePlan, mu_test, data_obs, ntoys, seed=0, toy_offset=
     mark("sampling")
     qq = qmu_tilde_batch(plan, mu_test, toys, init, lo, hi, fixed, mode, **fit_kw)
     mark("toy_fits")
-    q2 = qq["q"].reshape(2, ntoys)
+    # toys whose fits did not converge carry no test statistic: the reference raises
+    # FailedMinimization there (optimize/mixins.py:64-68); here they are marked NaN BEFORE the
+    # gather, left out of the p-value counts and denominators, and reported (every rank sees the
+    # same global count)
+    bad = (qq["fixed"].status != 0) | (qq["free"].status != 0)
+    q2 = torch.where(bad, torch.full_like(qq["q"], float("nan")), qq["q"]).reshape(2, ntoys)
     if gather is not None:
         q2 = gather(q2)          # one collective for both hypotheses
-    q_sig, q_bkg = q2[0].contiguous(), q2[1].contiguous()
     mark("gather")
+    keep = torch.isfinite(q2)
+    n_failed = int((~keep).sum())
+    if max_failed_fraction is not None and n_failed > max_failed_fraction * q2.numel():
+        raise RuntimeError(f"{n_failed} of {q2.numel()} toys have a failed fit")
+    q_sig, q_bkg = q2[0][keep[0]].contiguous(), q2[1][keep[1]].contiguous()
     n_sb = pvalue_counts(q_sig, qobs)[0].item()
     n_b = pvalue_counts(q_bkg, qobs)[0].item()
-    clsb = n_sb / q_sig.numel()
-    clb = n_b / q_bkg.numel()
+    clsb = n_sb / max(q_sig.numel(), 1)
+    clb = n_b / max(q_bkg.numel(), 1)
     mark("pvalues")
     expected = None
     if return_expected_set:
         expected = empirical_expected_pvalues(q_sig, q_bkg)
         mark("expected_band")
     return dict(qobs=float(qobs[0]), CLsb=clsb, CLb=clb, CLs=(clsb / clb if clb > 0 else float("nan")),
-                q_sig=q_sig, q_bkg=q_bkg, obs=obs, gen=gen, expected=expected,
-                n_failed=int((qq["fixed"].status != 0).sum() + (qq["free"].status != 0).sum()))
+                q_sig=q_sig, q_bkg=q_bkg, obs=obs, gen=gen, expected=expected, n_failed=n_failed,
+                n_iter_mean=float(torch.cat([qq["fixed"].niter, qq["free"].niter]).double().mean()))
 
 
 def asymptotic_pvalues(qmu, qmuA, test_stat="qtilde", calc_base_dist="normal"):

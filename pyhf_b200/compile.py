@@ -88,6 +88,19 @@ def compile_spec(spec, poi_name="mu", modifier_settings=None, clip_sample_data=N
     bin_seg = np.concatenate([np.full(nbins[c], i, np.int32) for i, c in enumerate(channels)])
     helper = {c: {s["name"]: (s, {f"{m['type']}/{m['name']}": m for m in s["modifiers"]})
                   for s in chan_specs[c]["samples"]} for c in channels}
+    # modifier types whose parameter set may not be shared (pdf.py:116-135; shapesys.py:40): a
+    # shapesys name reused on another sample or channel is an error, not one shared set
+    keys_seen = set()
+    for c in spec["channels"]:
+        for s in c["samples"]:
+            mine = set()
+            for m in s["modifiers"]:
+                key = f"{m['type']}/{m['name']}"
+                if m["type"] == "shapesys" and (key in keys_seen or key in mine):
+                    raise PlanError(f"Trying to add paramset {key} on {s['name']} sample in {c['name']} channel "
+                                    "but other paramsets exist with the same name.")
+                mine.add(key)
+            keys_seen |= mine
 
     nominal = np.zeros((S, NB))
     # per (modifier key, sample): data arrays over all bins
@@ -120,7 +133,7 @@ def compile_spec(spec, poi_name="mu", modifier_settings=None, clip_sample_data=N
                 d["mask"][si, sl] = True
                 if t in ("histosys", "normsys"):
                     required[t].setdefault(n, dict(kind="normal", n=1, inits=[0.0], bounds=[[-5.0, 5.0]],
-                                                   fixed=[False], auxdata=[0.0], sigmas=None))
+                                                   fixed=[False], auxdata=[0.0]))  # no "sigmas" key: not configurable
                 elif t == "normfactor":
                     required[t].setdefault(n, dict(kind="free", n=1, inits=[1.0], bounds=[[0.0, 10.0]],
                                                    fixed=[False]))
@@ -162,9 +175,12 @@ def compile_spec(spec, poi_name="mu", modifier_settings=None, clip_sample_data=N
     for t in TYPE_ORDER:
         for n, req in required[t].items():
             if n in parsets:
+                # parameters/utils.py:26-46: every property of the requirements must agree
                 a, b = parsets[n], req
-                if (a["kind"], a["n"]) != (b["kind"], b["n"]):
-                    raise PlanError(f"Multiple values for paramset {n}: use unique modifier names")
+                for k in ("kind", "n", "inits", "bounds", "auxdata", "factors", "sigmas", "fixed"):
+                    if a.get(k, "undefined") != b.get(k, "undefined"):
+                        raise PlanError(f"Multiple values for '{k}' were found for {n}. Use unique modifier "
+                                        "names when constructing the pdf.")
                 continue
             parsets[n] = dict(req)
     if not parsets:

@@ -255,6 +255,7 @@ void hf_plan_destroy(hf_plan* plan) {
     cudaFree(plan->dconst);
     if (plan->h_counters) cudaFreeHost(plan->h_counters);
     cudaFree(plan->fit_block);
+    cudaFree(plan->hess_block);
     cudaFree(plan->stage_block);
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
     if (plan->s_in) cudaStreamDestroy(plan->s_in);

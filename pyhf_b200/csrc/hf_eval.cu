@@ -678,7 +678,7 @@ hf_finish_grad_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
                         for (int i = 0; i < FIN_PPT; ++i) dl[i] = hf_sf_dlog_code4(cf, th[i]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < FIN_PPT; ++i) dl[i] = (th[i] > 0.0) ? cf[0] : -cf[1];
+                        for (int i = 0; i < FIN_PPT; ++i) dl[i] = (th[i] >= 0.0) ? cf[0] : -cf[1];  // right-sided at the kink
                     }
                     if (x_in_smem) {
 #pragma unroll

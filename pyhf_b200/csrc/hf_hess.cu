@@ -85,17 +85,22 @@ extern "C" int hf_hessian(hf_plan* plan, const double* pars, const double* data,
     const int64_t per = 2 * (int64_t)P;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 16) / per));
     const size_t npts = (size_t)chunk * per;
-    double *XP = nullptr, *GP = nullptr, *VP = nullptr;
-    int* ridx = nullptr;
-    auto release = [&]() { cudaFree(XP); cudaFree(GP); cudaFree(VP); cudaFree(ridx); };
-    if (cudaMalloc(&XP, sizeof(double) * npts * P) != cudaSuccess ||
-        cudaMalloc(&GP, sizeof(double) * npts * P) != cudaSuccess ||
-        cudaMalloc(&VP, sizeof(double) * npts) != cudaSuccess ||
-        cudaMalloc(&ridx, sizeof(int) * npts) != cudaSuccess) {
-        release();
-        hf_set_error("cudaMalloc for the Hessian workspace failed");
-        return HF_ERR_NOMEM;
+    // workspace kept in the plan (grown on demand, freed with the plan): XP | GP | VP | ridx
+    const size_t need = sizeof(double) * (2 * npts * P + npts) + sizeof(int) * npts + 1024;
+    if (need > plan->hess_bytes) {
+        if (plan->hess_block) cudaFree(plan->hess_block);
+        plan->hess_block = nullptr;
+        plan->hess_bytes = 0;
+        if (cudaMalloc(&plan->hess_block, need) != cudaSuccess) {
+            hf_set_error("cudaMalloc(%zu) for the Hessian workspace failed", need);
+            return HF_ERR_NOMEM;
+        }
+        plan->hess_bytes = need;
     }
+    double* XP = reinterpret_cast<double*>(plan->hess_block);
+    double* GP = XP + npts * P;
+    double* VP = GP + npts * P;
+    int* ridx = reinterpret_cast<int*>(VP + npts);
     int rc = HF_OK;
     for (int64_t b0 = 0; b0 < B && rc == HF_OK; b0 += chunk) {
         const int64_t nb = std::min<int64_t>(chunk, B - b0);
@@ -109,12 +114,7 @@ extern "C" int hf_hessian(hf_plan* plan, const double* pars, const double* data,
             P, nb, XP, GP, fixed, b0, hess);
         plan->launches++;
     }
-    cudaError_t e = cudaStreamSynchronize(st);  // the workspace is freed below
-    release();
     if (rc) return rc;
-    if (e != cudaSuccess) {
-        hf_set_error("hf_hessian: %s", cudaGetErrorString(e));
-        return HF_ERR_CUDA;
-    }
+    HF_CUDA_OK(cudaGetLastError());
     return HF_OK;
 }

@@ -98,8 +98,13 @@ __host__ __device__ inline void hf_hs_coeffs(int code, double a, double& c1, dou
         const bool pos = a > 0.0;
         c1 = pos ? a : 0.0;
         c2 = pos ? 0.0 : a;
-        dc1 = pos ? 1.0 : 0.0;
-        dc2 = pos ? 0.0 : 1.0;
+        // the derivative AT the kink alpha == 0 is the right-sided one: that is what the forward
+        // differences of the reference's SLSQP (optimize/opt_scipy.py:96-105, jac=None) see from
+        // suggested_init, and it decides which side of the kink a fit starts into (the reference's
+        // validation model 2bin_2channel_coupledhistosys has a cusp maximum there)
+        const bool dpos = a >= 0.0;
+        dc1 = dpos ? 1.0 : 0.0;
+        dc2 = dpos ? 0.0 : 1.0;
     }
 }
 
@@ -126,7 +131,8 @@ __host__ __device__ inline void hf_sf_eval(int kind, const double* __restrict__ 
         dl = dpoly / poly;
         return;
     }
-    const bool up = (kind == HF_SF_CODE4) ? (t >= 1.0) : (t > 0.0);
+    // (code1 at its kink t == 0: f = 1 from either branch, derivative right-sided -- see hf_hs_coeffs)
+    const bool up = (kind == HF_SF_CODE4) ? (t >= 1.0) : (t >= 0.0);
     if (up) {
         f = exp(t * lnu);
         dl = lnu;
@@ -201,7 +207,7 @@ __device__ __forceinline__ double hf_sf_dlog_code4(const double* __restrict__ cf
 // dlog f / dtheta of a normsys entry (kind != THETA)
 __device__ __forceinline__ double hf_sf_dlog(int kind, const double* __restrict__ cf, double t) {
     if (kind == HF_SF_CODE4) return hf_sf_dlog_code4(cf, t);  // kind is uniform across the warp
-    return (t > 0.0) ? cf[0] : -cf[1];
+    return (t >= 0.0) ? cf[0] : -cf[1];  // right-sided at the kink of code1
 }
 
 // main / constraint Poisson term without the theta-independent lgamma(n+1):
@@ -241,6 +247,9 @@ struct hf_plan {
     // fit workspace
     void* fit_block = nullptr;
     size_t fit_bytes = 0;
+    // workspace of hf_hessian
+    void* hess_block = nullptr;
+    size_t hess_bytes = 0;
     // staging for the *_host entry points
     void* stage_block = nullptr;
     size_t stage_bytes = 0;

@@ -11,7 +11,10 @@ to install a thin, reversible wrapper around ``pyhf.pdf.Model.logpdf`` that
 * performs the same shape checks / exceptions as the reference (pdf.py:969-981);
 * otherwise defers to the original method.
 
-The wrapper removes itself when ``tensorlib_changed`` fires for another backend.
+``Model.expected_data`` (pdf.py:886-906) gets the same treatment (``hf_expected_data``): it is what
+``generate_asimov_data`` calls between the fits of an asymptotic hypotest.
+
+The wrappers remove themselves when ``tensorlib_changed`` fires for another backend.
 """
 from __future__ import annotations
 
@@ -19,7 +22,7 @@ import logging
 
 log = logging.getLogger(__name__)
 
-_state = {"orig": None, "subscribed": False}
+_state = {"orig": None, "orig_expected": None, "subscribed": False}
 
 
 def _is_b200(tensorlib):
@@ -67,6 +70,33 @@ def install(backend):
         pyhf.pdf.Model.logpdf = logpdf
         _state["orig"] = orig
 
+        orig_expected = pyhf.pdf.Model.expected_data
+
+        def expected_data(self, pars, include_auxdata=True):  # same signature as pdf.py:886
+            # Asimov data (infer/calculators.py:45-97) and the toy-generation points go through here:
+            # one hf_expected_data launch instead of ~30 eager tensor ops
+            tensorlib, _ = pyhf.get_backend()
+            if not _is_b200(tensorlib) or self.batch_size is not None or getattr(pars, "requires_grad", False):
+                return orig_expected(self, pars, include_auxdata)
+            try:
+                plan = batched.plan_for(self, tensorlib.device)
+            except PlanError:
+                return orig_expected(self, pars, include_auxdata)
+            pars = tensorlib.astensor(pars)
+            if pars.shape[-1] != self.config.npars:  # pdf.py:899-901
+                msg = (f"Evaluation failed as parameters have length {pars.shape[-1]} but model requires "
+                       f"{self.config.npars}.")
+                raise exceptions.InvalidPdfParameters(msg)
+            if pars.dim() != 1:
+                return orig_expected(self, pars, include_auxdata)
+            out = tensorlib.astensor(plan.expected_data(pars))
+            return out if include_auxdata else out[: self.config.nmaindata]
+
+        expected_data.__wrapped__ = orig_expected
+        expected_data.__doc__ = orig_expected.__doc__
+        pyhf.pdf.Model.expected_data = expected_data
+        _state["orig_expected"] = orig_expected
+
     if not _state["subscribed"]:
         # module-level function: pyhf.events keeps plain functions by weak reference as well
         pyhf.events.subscribe("tensorlib_changed")(_on_tensorlib_changed)
@@ -79,6 +109,9 @@ def uninstall():
     if _state["orig"] is not None:
         pyhf.pdf.Model.logpdf = _state["orig"]
         _state["orig"] = None
+    if _state["orig_expected"] is not None:
+        pyhf.pdf.Model.expected_data = _state["orig_expected"]
+        _state["orig_expected"] = None
 
 
 def _on_tensorlib_changed():

@@ -62,6 +62,10 @@ class B200Optimizer:
         base = data._base
         if base is None or base.numel() == data.numel() or base.numel() % D != 0:
             return None
+        if not getattr(base, "_hf_toys", False):
+            # only storage the backend's samplers created is a toy batch (backend.mark_toys): a row
+            # of a user's own data matrix is fitted on its own
+            return None
         N = base.numel() // D
         stride = data.stride(0)
         off = data.storage_offset() - base.storage_offset()
@@ -126,7 +130,8 @@ class B200Optimizer:
         for idx, val in fixed_vals or []:  # infer/mle.py:128-132; opt_scipy.py:85-94
             fixed[idx] = 1
             init[idx] = float(val)
-        sig = (id(pdf), init.tobytes(), bounds.tobytes(), fixed.tobytes(),
+        # (the plan object is kept alive by the cache entry, so its id cannot be recycled)
+        sig = (id(plan), init.tobytes(), bounds.tobytes(), fixed.tobytes(),
                tuple(sorted((k, str(v)) for k, v in opts.items())))
 
         toy = self._toy_batch_of(data, D)
@@ -137,7 +142,7 @@ class B200Optimizer:
             if hit is None:
                 res = self._fit(plan, matrix.contiguous(), init, bounds[:, 0], bounds[:, 1], fixed, opts)
                 # the entry keeps ``base`` alive so its address cannot be recycled while cached
-                hit = (res.x, res.fun, res.status.cpu().numpy(), res.niter.cpu().numpy(), base)
+                hit = (res.x, res.fun, res.status.cpu().numpy(), res.niter.cpu().numpy(), base, plan)
                 if len(self._cache) > 8:
                     self._cache.pop(next(iter(self._cache)))
                 self._cache[ckey] = hit

@@ -119,7 +119,7 @@ def golden_names(with_plan_only=False):
     out = []
     for p in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         n = os.path.basename(p)[:-4]
-        if n in ("hello_toys", "scan_2bin_2channel"):
+        if n in ("hello_toys", "scan_2bin_2channel", "teststats", "c4_fits"):
             continue
         out.append(n)
     return out

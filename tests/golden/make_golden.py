@@ -549,6 +549,66 @@ def stage_edge():
 
 
 
+def stage_teststats():
+    """every test statistic of infer/test_statistics.py (qmu :63-153, qmu_tilde :156-254, tmu
+    :257-341, tmu_tilde :344-436, q0 :439-523) on the hello-world model and on the all-modifier
+    model: observed data + 7 toys each, tight reference optimizer.  The unbounded-POI statistics
+    (qmu, tmu) use POI bounds [-10, 10] as the reference's docstrings do (:96-97)."""
+    import warnings
+
+    ts = pyhf.infer.test_statistics
+    out = {}
+    specs = {}
+    for key in ("hello", "mixed"):
+        if key == "hello":
+            spec = synth.spec_hello()
+            model = pyhf.Model(spec, poi_name="mu")
+            data = np.array([51.0, 48.0] + model.config.auxdata)
+        else:
+            spec, model = mixed_model()
+            np.random.seed(3)
+            data = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(model.config.suggested_init())).sample((1,))[0])
+        specs[key] = spec
+        init = model.config.suggested_init()
+        fixed = model.config.suggested_fixed()
+        b_tilde = model.config.suggested_bounds()
+        b_free = [list(b) for b in b_tilde]
+        b_free[model.config.poi_index] = [-10.0, 10.0]
+        np.random.seed(11)
+        gen = np.array(init, float)
+        gen[model.config.poi_index] = 0.5
+        toys = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(gen)).sample((7,)))
+        rows = np.vstack([data[None], toys])
+        pyhf.set_backend("numpy", pyhf.optimize.scipy_optimizer(tolerance=1e-12))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for name, fn, mu, bounds in (("qmu", ts.qmu, 1.0, b_free), ("qmu_tilde", ts.qmu_tilde, 1.0, b_tilde),
+                                         ("tmu", ts.tmu, 1.0, b_free), ("tmu_tilde", ts.tmu_tilde, 1.0, b_tilde),
+                                         ("q0", ts.q0, 0.0, b_tilde)):
+                vals, muhats = [], []
+                for r in rows:
+                    v, (fixed_pars, free_pars) = fn(mu, r, model, init, bounds, fixed, return_fitted_pars=True)
+                    vals.append(float(v))
+                    muhats.append(float(free_pars[model.config.poi_index]))
+                out[f"{key}__{name}"] = np.array(vals)
+                out[f"{key}__{name}_muhat"] = np.array(muhats)
+                out[f"{key}__{name}_lo"] = np.array([b[0] for b in bounds])
+                out[f"{key}__{name}_hi"] = np.array([b[1] for b in bounds])
+        pyhf.set_backend("numpy", "scipy")
+        out[f"{key}__rows"] = rows
+        plan = extract_plan(model)
+        for k, v in plan.arrays().items():
+            out[f"{key}__plan__{k}"] = v
+    out["meta_json"] = np.array(json.dumps(dict(name="teststats", models=list(specs))))
+    path = os.path.join(HERE, "teststats.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path))
+    for k in out:
+        if k.count("__") == 1 and not k.endswith(("_lo", "_hi", "rows", "muhat")) and k != "meta_json":
+            print(k, np.round(out[k], 4))
+
+
+
 if __name__ == "__main__":
     stages = sys.argv[1:] or ["small", "toys", "c4", "c3"]
     for st in stages:

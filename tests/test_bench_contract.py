@@ -23,7 +23,7 @@ def _run(args, env=None, timeout=600):
 
 @pytest.mark.needs_pyhf
 def test_reference_arm_prints_one_json_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--no-toys"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
@@ -35,6 +35,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["fd_equivalent_value"] == pytest.approx(d["value"] / 301)   # P + 1 forward differences
+    # both arms name the workload with the same string
+    import re
+
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert len(re.findall(r'"workload": WORKLOAD', src)) == 2
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
 
 

@@ -90,3 +90,51 @@ def test_compiler_matches_live_extraction_on_signal_group_models(case):
     for spec, poi in zip(specs, pois):
         _assert_same(compile_spec(spec, poi_name=poi).arrays(),
                      extract_plan(pyhf.Model(spec, poi_name=poi)).arrays())
+
+
+def test_compiler_enforces_the_reference_builder_checks():
+    """pdf.py:116-135 (a shapesys name may not be reused: is_shared = False),
+    parameters/utils.py:26-62 (all requirement properties of a shared name must agree; a modifier
+    type that does not use an attribute rejects a user value for it)"""
+    def chan(name, mods_b):
+        return {"name": name, "samples": [
+            {"name": "s", "data": [5.0, 6.0], "modifiers": [{"name": "mu", "type": "normfactor", "data": None}]},
+            {"name": "b", "data": [50.0, 60.0], "modifiers": mods_b}]}
+
+    shp = {"name": "shp", "type": "shapesys", "data": [3.0, 4.0]}
+    with pytest.raises(PlanError, match="other paramsets exist"):
+        compile_spec({"channels": [chan("c1", [shp]), chan("c2", [dict(shp)])]})
+    ns = {"name": "sys", "type": "normsys", "data": {"hi": 1.1, "lo": 0.9}}
+    spec = {"channels": [chan("c1", [ns])],
+            "parameters": [{"name": "sys", "sigmas": [2.0]}]}
+    with pytest.raises(PlanError, match="does not use the sigmas"):
+        compile_spec(spec)
+    # same name on a 2-bin shapefactor and a scalar normsys: n_parameters disagree
+    sf = {"name": "sys", "type": "shapefactor", "data": None}
+    with pytest.raises(PlanError, match="Multiple values"):
+        compile_spec({"channels": [chan("c1", [ns, sf])]})
+    # histosys + normsys sharing a name is fine (identical requirements)
+    hs = {"name": "sys", "type": "histosys", "data": {"hi_data": [55.0, 66.0], "lo_data": [45.0, 54.0]}}
+    assert compile_spec({"channels": [chan("c1", [ns, hs])]}).n_pars == 2
+
+
+@pytest.mark.needs_pyhf
+def test_reference_builder_raises_on_the_same_specs():
+    """the negative cases above are errors in the unmodified reference too"""
+    import pyhf
+
+    def chan(name, mods_b):
+        return {"name": name, "samples": [
+            {"name": "s", "data": [5.0, 6.0], "modifiers": [{"name": "mu", "type": "normfactor", "data": None}]},
+            {"name": "b", "data": [50.0, 60.0], "modifiers": mods_b}]}
+
+    shp = {"name": "shp", "type": "shapesys", "data": [3.0, 4.0]}
+    ns = {"name": "sys", "type": "normsys", "data": {"hi": 1.1, "lo": 0.9}}
+    sf = {"name": "sys", "type": "shapefactor", "data": None}
+    with pytest.raises(pyhf.exceptions.InvalidModel):
+        pyhf.Model({"channels": [chan("c1", [shp]), chan("c2", [dict(shp)])]}, poi_name="mu", validate=False)
+    with pytest.raises(pyhf.exceptions.InvalidModel):
+        pyhf.Model({"channels": [chan("c1", [ns])], "parameters": [{"name": "sys", "sigmas": [2.0]}]},
+                   poi_name="mu", validate=False)
+    with pytest.raises(pyhf.exceptions.InvalidNameReuse):
+        pyhf.Model({"channels": [chan("c1", [ns, sf])]}, poi_name="mu", validate=False)

@@ -7,7 +7,7 @@ from conftest import CLIPPED, FIT_GOLDENS
 from oracle import fit_proto as F
 
 
-@pytest.mark.parametrize("name", [n for n in FIT_GOLDENS if n != "val_2bin_2channel_coupledhistosys" and n not in CLIPPED])
+@pytest.mark.parametrize("name", [n for n in FIT_GOLDENS if n not in CLIPPED])
 def test_proto_matches_reference_fits(name, golden):
     g = golden(name)
     pl = g.oracle_plan()

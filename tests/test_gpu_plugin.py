@@ -52,11 +52,21 @@ def test_model_logpdf_goes_through_k1(b200, golden):
         model.logpdf(g["pars"][1][:-1], g["data"])
     with pytest.raises(pyhf.exceptions.InvalidPdfData):
         model.logpdf(g["pars"][1], g["data"][:-1])
-    # generic op route (unfused) agrees
+    # Model.expected_data (pdf.py:886-906) goes through hf_expected_data ...
+    before = plan.launch_count
     ed = model.expected_data(g["pars"][1])
+    assert plan.launch_count > before, "Model.expected_data did not reach hf_expected_data"
     assert np.allclose(ed.cpu().numpy(), g["expected_data"][1], rtol=1e-12)
+    ed_main = model.expected_data(g["pars"][1], include_auxdata=False)
+    assert np.allclose(ed_main.cpu().numpy(), g["expected_data"][1][: model.config.nmaindata], rtol=1e-12)
+    with pytest.raises(pyhf.exceptions.InvalidPdfParameters):
+        model.expected_data(g["pars"][1][:-1])
+    # ... and the generic op route (unfused, what make_pdf(...).expected_data() does) agrees
+    ed2 = model.make_pdf(pyhf.tensorlib.astensor(g["pars"][1])).expected_data()
+    assert np.allclose(ed2.cpu().numpy(), g["expected_data"][1], rtol=1e-12)
     pyhf.set_backend("numpy", "scipy")
     assert not hasattr(pyhf.pdf.Model.logpdf, "__wrapped__"), "hook must uninstall on backend change"
+    assert not hasattr(pyhf.pdf.Model.expected_data, "__wrapped__")
 
 
 @pytest.mark.parametrize("name", [n for n in SMALL if n.startswith("val_")])
@@ -64,8 +74,6 @@ def test_validation_cls(name, b200, golden):
     """the reference's own CLs goldens (tests/test_validation.py) through the plugin"""
     pyhf = b200
     g = golden(name)
-    if name == "val_2bin_2channel_coupledhistosys":
-        pytest.skip("bimodal likelihood: local minimum differs from SLSQP's (DESIGN.md)")
     model = g.model()
     obs, exp = pyhf.infer.hypotest(g.meta["mu_test"], g["data"].tolist(), model,
                                    test_stat=g.meta["test_stat"], return_expected_set=True)
@@ -114,6 +122,47 @@ def test_unchanged_toycalculator(b200, golden):
     # asymptotic value 0.0525; 300 toys -> MC error ~0.02
     assert abs(float(cls_obs) - 0.0525) < 0.08
     assert len(cls_exp) == 5
+
+
+def test_unchanged_toycalculator_exact_parity(cuda, golden):
+    """The reference's own toy-based hypotest, unchanged, under the plugin in exact-parity mode
+    (b200_backend(toy_rng="numpy"): toys drawn as the reference's numpy backend draws them,
+    tensor/numpy_backend.py:24-51, in the order of calculators.py:797-817): the same
+    np.random.seed(0) gives the reference's CLs_obs and expected band (300 + 300 toys, 1 200 toy fits
+    in the CUDA minimiser)."""
+    import pyhf
+
+    import pyhf_b200
+
+    g = golden("hello")
+    gt = golden("hello_toys")
+    pyhf.set_backend(pyhf_b200.b200_backend(toy_rng="numpy"), pyhf_b200.b200_optimizer())
+    try:
+        model = g.model()
+        data = [51.0, 48.0] + model.config.auxdata
+        np.random.seed(0)
+        n = int(gt["toycalc_ntoys"])
+        obs, exp = pyhf.infer.hypotest(1.0, data, model, test_stat="qtilde", calctype="toybased", ntoys=n,
+                                       track_progress=False, return_expected_set=True)
+        assert pyhf.optimizer._stats["batched_fits"] == 4 * n
+    finally:
+        pyhf.set_backend("numpy", "scipy")
+    assert abs(float(obs) - float(gt["toycalc_cls_obs_tight"])) < 1e-6
+    assert np.allclose([float(e) for e in exp], gt["toycalc_cls_exp_tight"], atol=1e-6, rtol=0)
+    assert abs(float(obs) - float(gt["toycalc_cls_obs"])) < 1e-6   # default-tolerance reference: same counts
+
+
+def test_user_data_rows_are_not_mistaken_for_a_toy_batch(b200, golden):
+    """a row of the user's own data matrix is fitted on its own (only storage the backend's
+    samplers created is recognised as a toy batch)"""
+    pyhf = b200
+    g = golden("hello")
+    model = g.model()
+    mine = torch.as_tensor(np.tile(g["data"], (5, 1)), device="cuda")
+    before = dict(pyhf.optimizer._stats)
+    pyhf.infer.mle.fit(mine[2], model)
+    assert pyhf.optimizer._stats["batched_fits"] == before["batched_fits"]
+    assert pyhf.optimizer._stats["single_fits"] == before["single_fits"] + 1
 
 
 def test_config2_asymptotic_scan_upper_limit(b200, golden):

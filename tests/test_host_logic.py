@@ -39,3 +39,32 @@ def test_shard_ranges_tile_the_toys():
             assert parts[0][0] == 0 and sum(c for _, c in parts) == n
             assert all(parts[r][0] + parts[r][1] == parts[r + 1][0] for r in range(world - 1))
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+@pytest.mark.needs_pyhf
+def test_toy_batches_are_tagged_where_they_are_created():
+    """Simultaneous.sample (probability.py:263-274) under the torch carrier: every row of the toy
+    matrix is recognised as row i of ONE tagged batch (through concatenate / einsum / gather of
+    _TensorViewer.stitch, tensor/common.py:40-52); rows of a user's own matrix are not"""
+    import pyhf
+
+    from pyhf_b200 import synth
+    from pyhf_b200.backend import TorchCarrierBackend
+    from pyhf_b200.optimizer import B200Optimizer
+
+    tb = TorchCarrierBackend()
+    pyhf.set_backend(tb)
+    try:
+        for spec in (synth.spec_hello(), synth.spec_c3()):
+            model = pyhf.Model(spec, poi_name="mu", validate=False)
+            D = model.config.nmaindata + model.config.nauxdata
+            toys = model.make_pdf(tb.astensor(model.config.suggested_init())).sample((7,))
+            got = [B200Optimizer._toy_batch_of(r, D) for r in toys]
+            assert all(x is not None for x in got)
+            assert [x[2] for x in got] == list(range(7))
+            assert len({x[0] for x in got}) == 1            # one batch key
+            assert torch.equal(got[3][1][3], toys[3])
+            user = torch.as_tensor(np.random.rand(5, D))
+            assert B200Optimizer._toy_batch_of(user[2], D) is None
+    finally:
+        pyhf.set_backend("numpy", "scipy")

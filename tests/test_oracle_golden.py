@@ -66,7 +66,7 @@ def test_known_answers_of_reference_tests(golden):
     HostPlan.from_arrays(g.plan_arrays())  # round trip
 
 
-@pytest.mark.parametrize("name", [n for n in FIT_GOLDENS if n != "val_2bin_2channel_coupledhistosys"])
+@pytest.mark.parametrize("name", FIT_GOLDENS)
 def test_oracle_tight_fit_matches_reference_fits(name, golden):
     g = golden(name)
     pl = g.oracle_plan()
