@@ -40,6 +40,10 @@ import sys as _sys  # noqa: E402
 _sys.stdout.flush()
 _JSON_OUT = _os.fdopen(_os.dup(1), "w")
 _os.dup2(2, 1)
+# the CPU reference legs run one single-threaded process per host core: BLAS / OpenMP pools inside
+# each of them would oversubscribe the cores (set before numpy is imported; workers inherit it)
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    _os.environ.setdefault(_v, "1")
 import os
 import subprocess
 import sys
@@ -427,6 +431,8 @@ def run_b200(args):
 
     # ---- the north star's second metric, at every N: toy-based hypotests sharded over the ranks
     toy_legs = {}
+    h2d_bytes = int(pars_h.numel() * 8 + data_h.numel() * 8)
+    d2h_bytes = int(grad_h.numel() * 8 + out_h.numel() * 8)
     if not args.no_toys:
         del pars, grad, out, pars_h, grad_h, out_h
         torch.cuda.empty_cache()
@@ -473,8 +479,7 @@ def run_b200(args):
                    "l2": "inputs larger than L2 (pars 157 MB + grad 157 MB per step)"},
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(pars_h.numel() * 8 + data_h.numel() * 8),
-                "d2h_bytes_per_step": int(grad_h.numel() * 8 + out_h.numel() * 8),
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "path": "hf_logpdf_grad_host (C-ABI, pinned host buffers)"},
         "roofline": roofline,
     }

@@ -189,6 +189,14 @@ int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,
 int hf_hessian(hf_plan* plan, const double* pars, const double* data, int64_t data_rows, int64_t B,
                const double* lo, const double* hi, const uint8_t* fixed, double* hess, void* stream);
 
+/* The same matrix in closed form (one CTA per point; the curvature the minimiser K3 uses): mode 2 =
+ * exact Hessian on the given data, mode 1 = Fisher matrix (Hessian on the Asimov data of each point,
+ * positive semi-definite).  Returns HF_ERR_UNSUPPORTED for plans outside its scope (clipping, more
+ * than 8 samples or 120 histosys modifiers, per-bin parameters acting on several bins): callers fall
+ * back to hf_hessian.  fixed may be NULL. */
+int hf_hessian_analytic(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
+                        int64_t B, const uint8_t* fixed, int32_t mode, double* hess, void* stream);
+
 /*
  * K4 Philox-4x32-10 toy sampler: out[i] ~ Pois(lambda(pars)) (x) Normal(theta, sigma) (x)
  * Pois(theta*factor), i = 0..N-1, counter = (seed, offset + i) so results do not depend on how

@@ -65,6 +65,7 @@ SIGNATURES = {
     "hf_fit_batch_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64,
                                     C.POINTER(FitOpts), _vp, _vp, _vp, _vp, _vp]),
     "hf_hessian": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hf_hessian_analytic": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),
     "hf_sample_toys": (C.c_int, [_vp, _vp, _u64, _u64, _i64, _vp, _vp]),
     "hf_sample_poisson": (C.c_int, [_vp, _i64, _i64, _u64, _u64, _vp, _vp]),
     "hf_sample_normal": (C.c_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp]),

@@ -251,9 +251,11 @@ class DevicePlan:
         return FitResult(res.x[pick], res.fun[pick], res.status[pick], res.niter[pick])
 
     # ------------------------------------------------------------------ curvature
-    def hessian(self, pars, data, lo=None, hi=None, fixed=None):
-        """Hessian of 2*NLL at pars [B, P] (or [P]) by central differences of the analytic
-        gradient (hf_hessian); rows/columns of fixed parameters are the identity's."""
+    def hessian(self, pars, data, lo=None, hi=None, fixed=None, method="fd"):
+        """Hessian of 2*NLL at pars [B, P] (or [P]); rows/columns of fixed parameters are the
+        identity's.  ``method``: "fd" = central differences of the analytic gradient (hf_hessian);
+        "analytic" / "fisher" = the closed form the minimiser uses (hf_hessian_analytic: exact
+        Hessian / Fisher matrix = Hessian on the Asimov data of each point)."""
         dev = self.device
         pars = _dev_tensor(pars, dev)
         single = pars.dim() == 1
@@ -268,8 +270,15 @@ class DevicePlan:
         B = pars.shape[0]
         out = torch.empty(B, self.P, self.P, dtype=F64, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(self._lib.hf_hessian(self._h, _ptr(pars), _ptr(data), data.shape[0], B, _ptr(lo),
-                                            _ptr(hi), _ptr(fixed), _ptr(out), _stream()))
+            if method == "fd":
+                _lib.check(self._lib.hf_hessian(self._h, _ptr(pars), _ptr(data), data.shape[0], B, _ptr(lo),
+                                                _ptr(hi), _ptr(fixed), _ptr(out), _stream()))
+            elif method in ("analytic", "fisher"):
+                _lib.check(self._lib.hf_hessian_analytic(self._h, _ptr(pars), _ptr(data), data.shape[0], B,
+                                                         _ptr(fixed), 2 if method == "analytic" else 1,
+                                                         _ptr(out), _stream()))
+            else:
+                raise ValueError(f"unknown Hessian method {method}")
         return out[0] if single else out
 
     def covariance(self, pars, data, lo=None, hi=None, fixed=None):

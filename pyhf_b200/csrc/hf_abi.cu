@@ -204,6 +204,67 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     const size_t o_qgn = pk.add(qg_n.data(), sizeof(int32_t) * qg_n.size());
     const size_t o_ck = pk.add(cons_kind.data(), sizeof(int32_t) * P);
     const size_t o_ci = pk.add(cons_idx.data(), sizeof(int32_t) * P);
+    // ---- analytic-Hessian tables and qualification (hf_hess_analytic.cu)
+    bool ah_ok = !d->has_clip_sample && !d->has_clip_bin && S <= HF_AH_SMAX && H <= 120 && R <= HF_AH_SMAX;
+    std::vector<int32_t> sfp_list, sf_j(NSF, 0), par_j(P, -1), bl_ptr(NB + 1, 0), bl_par, seg_first(NSEG + 1, NB);
+    std::vector<uint32_t> bl_mask;
+    std::vector<uint8_t> par_mult(P, 0);
+    {
+        for (int e = 0; e < NSF; ++e) {
+            const int p = d->sf_par[e];
+            if (par_j[p] < 0) { par_j[p] = (int)sfp_list.size(); sfp_list.push_back(p); }
+            sf_j[e] = par_j[p];
+            if (d->sf_kind[e] == HF_SF_THETA) par_mult[p] = 1;
+        }
+        // one entry per (sample, segment, parameter)
+        for (int q = 0; ah_ok && q < S * NSEG; ++q)
+            for (int e = d->sf_ptr[q]; ah_ok && e < d->sf_ptr[q + 1]; ++e)
+                for (int e2 = e + 1; e2 < d->sf_ptr[q + 1]; ++e2)
+                    if (d->sf_par[e] == d->sf_par[e2]) ah_ok = false;
+        // bins of a segment are contiguous
+        for (int b = 0; b < NB; ++b) {
+            if (b > 0 && d->bin_seg[b] < d->bin_seg[b - 1]) ah_ok = false;
+            seg_first[d->bin_seg[b]] = std::min(seg_first[d->bin_seg[b]], b);
+        }
+        for (int c = NSEG - 1; c >= 0; --c)
+            if (seg_first[c] == NB) seg_first[c] = seg_first[c + 1];  // empty segment
+        // per-bin parameters: each acts on exactly one bin, is no scalar-factor / histosys parameter,
+        // and multiplies a cell at most once
+        std::vector<int32_t> bin_of(P, -1);
+        std::vector<char> is_glob(P, 0);
+        for (int h = 0; h < H; ++h) is_glob[d->hs_par[h]] = 1;
+        for (int e = 0; e < NSF; ++e) is_glob[d->sf_par[e]] = 1;
+        for (int b = 0; b < NB; ++b) {
+            std::vector<int32_t> here;
+            std::vector<uint32_t> mk;
+            for (int s2 = 0; s2 < S; ++s2)
+                for (int k = 0; k < K; ++k) {
+                    const int p = d->bf_par[((size_t)k * S + s2) * NB + b];
+                    if (p < 0) continue;
+                    par_mult[p] = 1;
+                    if (is_glob[p] || (bin_of[p] >= 0 && bin_of[p] != b)) ah_ok = false;
+                    bin_of[p] = b;
+                    size_t i = 0;
+                    while (i < here.size() && here[i] != p) ++i;
+                    if (i == here.size()) { here.push_back(p); mk.push_back(0u); }
+                    if (s2 < 32) {
+                        if (mk[i] & (1u << s2)) ah_ok = false;  // the same parameter twice on one cell
+                        mk[i] |= 1u << s2;
+                    }
+                }
+            if ((int)here.size() > HF_AH_KLMAX) ah_ok = false;
+            bl_ptr[b + 1] = bl_ptr[b] + (int)here.size();
+            bl_par.insert(bl_par.end(), here.begin(), here.end());
+            bl_mask.insert(bl_mask.end(), mk.begin(), mk.end());
+        }
+    }
+    const size_t o_ahl = pk.add(sfp_list.data(), sizeof(int32_t) * sfp_list.size());
+    const size_t o_ahj = pk.add(sf_j.data(), sizeof(int32_t) * NSF);
+    const size_t o_ahbp = pk.add(bl_ptr.data(), sizeof(int32_t) * (NB + 1));
+    const size_t o_ahbq = pk.add(bl_par.data(), sizeof(int32_t) * bl_par.size());
+    const size_t o_ahbm = pk.add(bl_mask.data(), sizeof(uint32_t) * bl_mask.size());
+    const size_t o_ahsf = pk.add(seg_first.data(), sizeof(int32_t) * (NSEG + 1));
+    const size_t o_ahpm = pk.add(par_mult.data(), P);
     pk.add(nullptr, 256);
 
     cudaError_t e = cudaMalloc(&plan->table_block, pk.host.size());
@@ -238,6 +299,10 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     dp.mma_ok = mma_ok ? 1 : 0; dp.mma_ntiles = mma_ntiles; dp.mma_nchunks = mma_nchunks;
     dp.mma_nother = n_other; dp.mma_other[0] = other[0]; dp.mma_other[1] = other[1];
     dp.mma_tt = DP(double, o_tt);
+    dp.ah_ok = ah_ok ? 1 : 0; dp.ah_nsfp = (int)sfp_list.size(); dp.ah_nbl = (int)bl_par.size();
+    dp.ah_sfp_list = DP(int, o_ahl); dp.ah_sf_j = DP(int, o_ahj); dp.ah_bl_ptr = DP(int, o_ahbp);
+    dp.ah_bl_par = DP(int, o_ahbq); dp.ah_bl_mask = DP(unsigned, o_ahbm); dp.ah_seg_first = DP(int, o_ahsf);
+    dp.ah_par_mult = DP(unsigned char, o_ahpm);
 #undef DP
     plan->h_bf_par.assign(d->bf_par, d->bf_par + (size_t)K * S * NB);
     plan->h_hs_par.assign(d->hs_par, d->hs_par + H);

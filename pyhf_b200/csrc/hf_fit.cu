@@ -40,6 +40,13 @@ struct FitDev {
     int *done, *need_dir, *own, *status, *niter, *refresh, *rlist, *counters;
     int *nfail, *force, *rlist2;  // consecutive rejections, (unused), second request list
     int* pending;  // fit waits for its Fisher fallback (computed at the top of the next round)
+    int* ownstart; // start point differs from fit 0's: the fit gets its own start-up curvature
+    // saddle escape: a fit that meets the stopping rule at a point whose Hessian is NOT positive
+    // definite (the factorisation needed a shift) sits on a saddle or a ridge, typically by an exact
+    // symmetry of the start point (two systematics with identical templates): it is displaced by a
+    // small deterministic perturbation and carries on (at most twice)
+    int *indef, *nkick, *kick;  // last factorisation needed a shift | kicks so far | 1 = kick trial in flight, 2 = requested
+    int* nindef;                // consecutive near-stationary directions (edm < 1e-3) whose Hessian needed a shift
     double* damp;                 // Levenberg-Marquardt damping added to the diagonal (0 = pure Newton)
     int *live, *live_next;   // compacted list of fits still running (order is arbitrary)
     const int* islocal;      // [P] 1 when the parameter only couples to the global block (diagonal local block)
@@ -86,10 +93,16 @@ __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64
     if (!fit_mask(s, i)[p]) v = fmin(fmax(v, s.lo[p]), s.hi[p]);
     s.X[idx] = v;
     s.XT[idx] = v;
+    if (init_rows != 1 && i > 0) {
+        double v0 = init[p];
+        if (!fit_mask(s, 0)[p]) v0 = fmin(fmax(v0, s.lo[p]), s.hi[p]);
+        if (v != v0) s.ownstart[i] = 1;  // (benign race: every writer stores 1)
+    }
     if (p == 0) {
         s.done[i] = 0; s.need_dir[i] = 1; s.own[i] = 0; s.status[i] = 1; s.niter[i] = 0;
         s.refresh[i] = 0; s.T[i] = 1.0; s.EDM[i] = INFINITY; s.EDMPREV[i] = INFINITY;
         s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = s.damp0; s.pending[i] = 0;
+        s.indef[i] = 0; s.nkick[i] = 0; s.kick[i] = 0; s.nindef[i] = 0;
     }
 }
 
@@ -248,6 +261,32 @@ __device__ bool chol_factor(double* A, int n, int nloc, int tid, int nth) {
     return true;
 }
 
+constexpr int kMaxKicks = 2;
+
+// displacement that breaks an exact symmetry of the current point (see FitDev::indef)
+__device__ void fit_write_kick(const FitDev& s, int64_t toy, int tid, int nth) {
+    const int P = s.P;
+    double* d = s.Dd + toy * P;
+    const double* x = s.X + toy * P;
+    const uint8_t* mask = fit_mask(s, toy);
+    const unsigned salt = 40503u * (unsigned)(s.nkick[toy] + 1);
+    for (int p = tid; p < P; p += nth) {
+        const unsigned hsh = ((unsigned)(p + 1) * 2654435761u + salt) >> 8;
+        const double u = (double)(hsh & 0xffffu) / 32768.0 - 1.0;
+        d[p] = mask[p] ? 0.0 : 1e-3 * fmax(1.0, fabs(x[p])) * u;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s.T[toy] = 1.0;
+        s.need_dir[toy] = 0;
+        s.pending[toy] = 0;
+        s.kick[toy] = 1;
+        s.nkick[toy] += 1;
+        s.own[toy] = 0;  // the next direction pass asks for the exact Hessian of the displaced point
+        s.damp[toy] = 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(kDirThreads)
 fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int allow_refresh) {
     extern __shared__ __align__(16) double sm[];
@@ -256,6 +295,7 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     const int64_t toy = list ? (int64_t)list[blockIdx.x] : (int64_t)blockIdx.x;
     if (toy >= s.NC) return;
     if (s.done[toy] || !s.need_dir[toy]) return;
+    if (s.kick[toy] == 2) { fit_write_kick(s, toy, tid, nth); return; }
 
     // shared layout: b[P] | map[P] (int) | packed A (if it fits)
     double* bvec = sm;
@@ -306,7 +346,9 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
 
     double tau = s.damp[toy];  // Levenberg-Marquardt damping carried by the fit (0 = pure Newton)
     bool ok = false;
+    int attempts = 0;
     for (int attempt = 0; attempt < 40 && !ok; ++attempt) {
+        ++attempts;
         // rows of the packed lower triangle; off-diagonal entries of the local block are never
         // read (they are structurally zero) and are not loaded
         for (int i = tid; i < nloc; i += nth) A[tri(i, i)] = Hsrc[(int64_t)fidx[i] * P + fidx[i]] + tau;
@@ -408,15 +450,23 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     for (int p = tid; p < P; p += nth) d[p] = 0.0;
     __syncthreads();
     for (int i = tid; i < n; i += nth) d[fidx[i]] = bvec[i];
+    const bool converged = isfinite(edm) && edm < s.tol_edm && step < s.tol_step;
+    // creeping along a ridge: nearly stationary, Hessian not positive definite, several times in a row
+    const int ncreep = (attempts > 1 && isfinite(edm) && edm < 1e-3) ? s.nindef[toy] + 1 : 0;
+    const bool saddle = ((converged && attempts > 1) || ncreep >= 4) && s.nkick[toy] < kMaxKicks;
+    __syncthreads();
     if (tid == 0) {
+        s.nindef[toy] = saddle ? 0 : ncreep;
         s.EDM[toy] = edm;
         s.EDMPREV[toy] = edm;
         s.T[toy] = 1.0;
         s.need_dir[toy] = 0;
         s.pending[toy] = 0;
+        s.indef[toy] = attempts > 1 ? 1 : 0;
         if (!isfinite(edm)) { s.done[toy] = 1; s.status[toy] = 2; }
-        else if (edm < s.tol_edm && step < s.tol_step) { s.done[toy] = 1; s.status[toy] = 0; }
+        else if (converged && !saddle) { s.done[toy] = 1; s.status[toy] = 0; }
     }
+    if (saddle) { __syncthreads(); fit_write_kick(s, toy, tid, nth); }
 }
 
 // ---------------------------------------------------------------- Newton direction, Schur form
@@ -443,6 +493,7 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
     const int64_t toy = (int64_t)list[blockIdx.x];
     if (toy >= s.NC) return;
     if (s.done[toy] || !s.need_dir[toy]) return;
+    if (s.kick[toy] == 2) { fit_write_kick(s, toy, tid, nth); return; }
 
     const int ngp = ngmax | 1;
     double* S = sm;                                  // packed lower triangle of the reduced matrix
@@ -676,15 +727,23 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
     __syncthreads();
     for (int i = tid; i < nl; i += nth) d[loc[i]] = gl[i];
     for (int a = tid; a < ng; a += nth) d[glb[a]] = r[a];
+    const bool converged = isfinite(edm) && edm < s.tol_edm && step < s.tol_step;
+    // creeping along a ridge: nearly stationary, Hessian not positive definite, several times in a row
+    const int ncreep = (attempts > 1 && isfinite(edm) && edm < 1e-3) ? s.nindef[toy] + 1 : 0;
+    const bool saddle = ((converged && attempts > 1) || ncreep >= 4) && s.nkick[toy] < kMaxKicks;
+    __syncthreads();
     if (tid == 0) {
+        s.nindef[toy] = saddle ? 0 : ncreep;
         s.EDM[toy] = edm;
         s.EDMPREV[toy] = edm;
         s.T[toy] = 1.0;
         s.need_dir[toy] = 0;
         s.pending[toy] = 0;
+        s.indef[toy] = attempts > 1 ? 1 : 0;
         if (!isfinite(edm)) { s.done[toy] = 1; s.status[toy] = 2; }
-        else if (edm < s.tol_edm && step < s.tol_step) { s.done[toy] = 1; s.status[toy] = 0; }
+        else if (converged && !saddle) { s.done[toy] = 1; s.status[toy] = 0; }
     }
+    if (saddle) { __syncthreads(); fit_write_kick(s, toy, tid, nth); }
 }
 
 // ---------------------------------------------------------------- trial point / acceptance
@@ -725,8 +784,13 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
     const double f = s.F[toy];
     const double ft = -2.0 * VTc[k];
     const double slack = 4e-15 * fmax(1.0, fabs(f));
-    const bool ok = isfinite(ft) && (ft <= f + kArmijo * dec + slack);
+    const bool kicked = s.kick[toy] == 1;  // displaced off a saddle: taken unconditionally
+    const bool ok = isfinite(ft) && (kicked || ft <= f + kArmijo * dec + slack);
     bool alive = true;
+    if (kicked && !ok) {  // (not even finite: stay where the fit was)
+        if (lane == 0) { s.done[toy] = 1; s.status[toy] = 0; s.kick[toy] = 0; }
+        return;
+    }
     if (s.trace && (nl <= 3 || toy < 2) && lane == 0)
         printf("[hf_fit trace] fit %lld it %d f %.12g ft-f %.3e dec %.3e edm %.3e damp %.3e own %d refresh %d nfail %d %s\n",
                (long long)toy, s.niter[toy], f, ft - f, dec, s.EDM[toy], s.damp[toy], s.own[toy], s.refresh[toy],
@@ -741,6 +805,7 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
             s.F[toy] = ft;
             s.need_dir[toy] = 1;
             s.nfail[toy] = 0;
+            s.kick[toy] = 0;
             const double dmp = 0.2 * s.damp[toy];
             s.damp[toy] = (dmp < 1e-6) ? 0.0 : dmp;
             const int it = s.niter[toy] + 1;
@@ -752,7 +817,12 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
         // style) instead of shrinking the step along a direction a nearly singular Hessian made bad
         const int nr = s.nfail[toy] + 1;
         if (s.EDM[toy] < 1e-7) {  // predicted decrease below the rounding floor of f: converged
-            s.done[toy] = 1; s.status[toy] = 0; alive = false;
+            if (s.indef[toy] && s.nkick[toy] < kMaxKicks) {
+                s.kick[toy] = 2;  // ... on a saddle: the next direction pass displaces the fit
+                s.need_dir[toy] = 1;
+            } else {
+                s.done[toy] = 1; s.status[toy] = 0; alive = false;
+            }
         } else if (nr > 60) {
             s.done[toy] = 1; s.status[toy] = 2; alive = false;
         } else {
@@ -763,6 +833,14 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
         }
     }
     if (lane == 0 && alive) live_next[atomicAdd(&s.counters[1], 1)] = (int)toy;
+}
+
+// fits whose start point differs from fit 0's (their start-up curvature cannot be the shared matrix)
+__global__ void fit_ownstart_list_kernel(FitDev s, int* __restrict__ list, int* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.NC || !s.ownstart[i] || s.done[i]) return;
+    list[atomicAdd(count, 1)] = (int)i;
+    s.own[i] = 1;
 }
 
 __global__ void fit_iota_kernel(int* __restrict__ out, int64_t n) {
@@ -886,6 +964,11 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     int nfree = 0;
     for (int p = 0; p < P; ++p) nfree += h_fixed[p] ? 0 : 1;
 
+    // curvature: closed form (hf_hess_analytic.cu) when the plan qualifies, else forward differences
+    // of the analytic gradient
+    bool use_ah = plan->d.ah_ok != 0;
+    if (const char* e = getenv("HF_FIT_HESS")) use_ah = use_ah && e[0] != 'f';  // "fd": tuning / test knob
+    const size_t ah_stride = hf_hess_analytic_scratch_doubles(plan);
     // ---- chunking: per-fit Hessians dominate the memory
     size_t free_b = 0, total_b = 0;
     HF_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
@@ -893,8 +976,10 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     const size_t budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
     int64_t NC = std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)(budget / per_fit)));
     // FD batch: points per K2 launch
-    const int64_t max_pts = std::max<int64_t>((int64_t)(ncol + 1), std::min<int64_t>((int64_t)1 << 18,
+    const int64_t max_pts = use_ah ? (int64_t)(ncol + 1)
+                                   : std::max<int64_t>((int64_t)(ncol + 1), std::min<int64_t>((int64_t)1 << 18,
                                 (int64_t)(budget / (sizeof(double) * (2 * (size_t)P + 2) + 8))));
+    const int64_t ah_cap = std::max<int64_t>(1, std::min<int64_t>(NC, (int64_t)(((size_t)2 << 30) / (sizeof(double) * ah_stride))));
     const int64_t rl_cap = std::max<int64_t>(1, max_pts / (ncol + 1));  // refresh entries per sub-batch
 
     const size_t tri_bytes = sizeof(double) * (size_t)P * (P + 1) / 2;
@@ -903,6 +988,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     const int64_t dir_grid_cap = chol_in_smem ? 0 : std::min<int64_t>(NC, 4096);
 
     Carver cv{nullptr};
+    double* AHS = nullptr;  // scratch of the analytic-Hessian kernel, per request
     auto carve = [&](Carver& c, FitDev& s, double*& XP, double*& GP, double*& VP, double*& DR,
                      double*& AS, double*& XG, int*& ridx, int*& d_colpar, int*& d_pcolor,
                      int*& d_partner, int*& d_pcol, int*& d_islocal, uint8_t*& d_struct, double*& DC) {
@@ -917,7 +1003,11 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.live = c.take<int>(NC + 1); s.live_next = c.take<int>(NC + 1);
         s.nfail = c.take<int>(NC); s.force = c.take<int>(NC); s.rlist2 = c.take<int>(NC + 1);
         s.pending = c.take<int>(NC);
+        s.ownstart = c.take<int>(NC);
+        s.indef = c.take<int>(NC); s.nkick = c.take<int>(NC); s.kick = c.take<int>(NC);
+        s.nindef = c.take<int>(NC);
         s.damp = c.take<double>(NC);
+        AHS = use_ah ? c.take<double>((size_t)ah_cap * ah_stride) : nullptr;
         d_islocal = c.take<int>(P);
         d_struct = c.take<uint8_t>(P);
         DC = c.take<double>(data_rows);
@@ -1042,6 +1132,16 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
 
     auto run_hessians = [&](const int* d_list, int64_t nlist, const int* mode, int64_t toy0,
                             int to_shared, bool need_asimov = true) -> int {
+        if (use_ah) {
+            for (int64_t r0 = 0; r0 < nlist; r0 += ah_cap) {
+                const int64_t nl = std::min<int64_t>(ah_cap, nlist - r0);
+                int rc = hf_hess_analytic_launch(plan, s.X, d_list + r0, nullptr, (int)nl, mode, 1, data, data_rows,
+                                                 data_map, toy0, to_shared ? s.Hshared : s.H, to_shared, AHS,
+                                                 d_struct, st);
+                if (rc) return rc;
+            }
+            return HF_OK;
+        }
         for (int64_t r0 = 0; r0 < nlist; r0 += rl_cap) {
             const int64_t nl = std::min<int64_t>(rl_cap, nlist - r0);
             const int* lst = d_list + r0;
@@ -1076,6 +1176,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.toy0 = toy0;
         const double* init_c = init + (init_rows == 1 ? 0 : toy0 * P);
         const double* data_c = data + ((data_rows == 1 || data_map) ? 0 : toy0 * D);
+        HF_CUDA_OK(cudaMemsetAsync(s.ownstart, 0, sizeof(int) * nc, st));
         fit_init_kernel<<<blocks(nc * P, 256), 256, 0, st>>>(s, init_c, init_rows);
         plan->launches++;
         int rc = hf_eval_launch(plan, s.X, data_c, data_map ? data_rows : (data_rows == 1 ? 1 : nc), nc, s.VT,
@@ -1089,6 +1190,23 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
             HF_CUDA_OK(cudaMemcpyAsync(s.rlist, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
             rc = run_hessians(s.rlist, 1, nullptr, toy0, 1);
             if (rc) return rc;
+        }
+        if (use_ah && init_rows != 1) {
+            // fits that do not start where fit 0 starts get the Fisher matrix of their own start
+            // point (multistart, scans with the POI fixed at different values); device-side count
+            HF_CUDA_OK(cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st));
+            fit_ownstart_list_kernel<<<blocks(nc, 256), 256, 0, st>>>(s, s.rlist, s.counters + 6);
+            plan->launches++;
+            for (int64_t r0 = 0; r0 < nc; r0 += ah_cap) {
+                // (request r0 + i; the kernel leaves when r0 + i >= the device count)
+                rc = hf_hess_analytic_launch(plan, s.X, s.rlist + r0, s.counters + 6, (int)std::min<int64_t>(ah_cap, nc - r0),
+                                             nullptr, 1, data, data_rows, data_map, toy0, s.H, 0, AHS, d_struct, st);
+                if (rc) return rc;
+                if (r0 + ah_cap < nc) {  // next chunk: remaining count = max(count - ah_cap, 0)
+                    hf_set_error("own-start curvature for more than %lld fits per chunk is not supported", (long long)ah_cap);
+                    return HF_ERR_UNSUPPORTED;
+                }
+            }
         }
         fit_iota_kernel<<<blocks(nc, 256), 256, 0, st>>>(s.live, nc);
         plan->launches++;

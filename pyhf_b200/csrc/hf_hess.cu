@@ -118,3 +118,50 @@ extern "C" int hf_hessian(hf_plan* plan, const double* pars, const double* data,
     HF_CUDA_OK(cudaGetLastError());
     return HF_OK;
 }
+
+// Closed-form Hessian of 2*NLL (hf_hess_analytic.cu) at B points: mode 2 = exact (on the given data),
+// mode 1 = Fisher (on the Asimov data of each point).  HF_ERR_UNSUPPORTED when the plan does not
+// qualify (clipping, > 8 samples, > 120 histosys, per-bin parameters acting on several bins).
+extern "C" int hf_hessian_analytic(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
+                                   int64_t B, const uint8_t* fixed, int32_t mode, double* hess, void* stream) {
+    if (!plan || !pars || !data || !hess) {
+        hf_set_error("null argument");
+        return HF_ERR_INVALID;
+    }
+    if (B <= 0) return HF_OK;
+    if (data_rows != 1 && data_rows != B) {
+        hf_set_error("data_rows must be 1 or B");
+        return HF_ERR_INVALID;
+    }
+    if (mode != 1 && mode != 2) {
+        hf_set_error("mode must be 1 (Fisher) or 2 (exact)");
+        return HF_ERR_INVALID;
+    }
+    if (!plan->d.ah_ok) {
+        hf_set_error("plan does not qualify for the analytic Hessian");
+        return HF_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t stride = hf_hess_analytic_scratch_doubles(plan);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(((size_t)1 << 29) / (sizeof(double) * stride))));
+    const size_t need = sizeof(double) * stride * (size_t)chunk + 1024;
+    if (need > plan->hess_bytes) {
+        if (plan->hess_block) cudaFree(plan->hess_block);
+        plan->hess_block = nullptr;
+        plan->hess_bytes = 0;
+        if (cudaMalloc(&plan->hess_block, need) != cudaSuccess) {
+            hf_set_error("cudaMalloc(%zu) for the Hessian workspace failed", need);
+            return HF_ERR_NOMEM;
+        }
+        plan->hess_bytes = need;
+    }
+    const int P = plan->P;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, B - b0);
+        int rc = hf_hess_analytic_launch(plan, pars + b0 * P, nullptr, nullptr, (int)nb, nullptr, mode,
+                                         data, data_rows, nullptr, b0, hess + b0 * (int64_t)P * P, 0,
+                                         reinterpret_cast<double*>(plan->hess_block), fixed, st);
+        if (rc) return rc;
+    }
+    return HF_OK;
+}

@@ -52,7 +52,21 @@ struct DevPlan {
     int mma_nother;              // samples without histosys
     int mma_other[2];            // their sample indices
     const double* mma_tt;        // [ntiles][nchunks][HF_MMA_KC][HF_MMA_CS] (cell = bin_local*4 + row)
+    // ---- analytic Hessian (hf_hess_analytic.cu)
+    int ah_ok;                   // plan qualifies (else the minimiser differences the analytic gradient)
+    int ah_nsfp;                 // distinct parameters among the scalar-factor entries
+    int ah_nbl;                  // (bin, per-bin parameter) pairs
+    const int* ah_sfp_list;      // [ah_nsfp] parameter index
+    const int* ah_sf_j;          // [NSF] position of the entry's parameter in ah_sfp_list
+    const int* ah_bl_ptr;        // [NB+1] CSR over bins of the per-bin parameters acting there
+    const int* ah_bl_par;        // [ah_nbl]
+    const unsigned* ah_bl_mask;  // [ah_nbl] bit s: the parameter multiplies sample s on that bin
+    const int* ah_seg_first;     // [NSEG+1] first bin of a segment (bins of a segment are contiguous)
+    const unsigned char* ah_par_mult;  // [P] the parameter multiplies rates (normfactor / lumi / per-bin factor)
 };
+
+#define HF_AH_SMAX 8    // samples the analytic-Hessian kernel keeps in registers
+#define HF_AH_KLMAX 4   // per-bin parameters on one bin
 
 #define HF_MMA_BT 32    // bins per tile
 #define HF_MMA_NC 128   // cells per tile (4 rows per bin)
@@ -279,6 +293,20 @@ int hf_data_const_launch(hf_plan* plan, const double* data, int64_t rows, double
 // DMMA main kernel (hf_eval_mma.cu); returns HF_ERR_UNSUPPORTED when the plan does not qualify
 int hf_main_mma_launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_point,
                        const int* row_idx, bool grad, cudaStream_t st);
+// analytic Hessian of 2*NLL (hf_hess_analytic.cu); request i: point X[list ? list[i] : i], matrix
+// H[same row] (or the one shared matrix), mode 1 = Fisher / 2 = exact (per fit, or mode_all)
+size_t hf_hess_analytic_scratch_doubles(const hf_plan* plan);
+int hf_hess_analytic_launch(hf_plan* plan, const double* X, const int* list, const int* n_dev, int nreq,
+                            const int* mode, int mode_all, const double* data, int64_t data_rows,
+                            const int* data_map, int64_t toy0, double* Hout, int to_shared, double* scratch,
+                            const uint8_t* fixed_struct, cudaStream_t st);
+// analytic Hessian of 2*NLL (hf_hess_analytic.cu); request i: point X[list ? list[i] : i], matrix
+// H[same row] (or the one shared matrix), mode 1 = Fisher / 2 = exact (per fit, or mode_all)
+size_t hf_hess_analytic_scratch_doubles(const hf_plan* plan);
+int hf_hess_analytic_launch(hf_plan* plan, const double* X, const int* list, const int* n_dev, int nreq,
+                            const int* mode, int mode_all, const double* data, int64_t data_rows,
+                            const int* data_map, int64_t toy0, double* Hout, int to_shared, double* scratch,
+                            const uint8_t* fixed_struct, cudaStream_t st);
 static inline int hf_mma_ks(int H) {  // padded coefficient row stride, == 12 mod 16 doubles
     int ks = 2 * H;
     ks = (ks + HF_MMA_KC - 1) / HF_MMA_KC * HF_MMA_KC;

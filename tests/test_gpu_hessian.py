@@ -55,6 +55,73 @@ def test_hessian_matches_oracle_differences(name, golden, cuda):
         assert np.array_equal(H[k], H[k].T)
 
 
+@pytest.mark.parametrize("name", ["hello", "mixed_code4p_code4", "mixed_code0_code1", "val_2bin_2channel_couplednorm",
+                                  "val_2bin_2channel_coupledhistosys", "val_2bin_2channel_coupledshapefactor",
+                                  "val_1bin_lumi", "staterror_zero", "empty_signal_bin", "c3", "c4"])
+def test_closed_form_hessian_matches_differences_of_the_gradient(name, golden, cuda):
+    """hf_hessian_analytic (the curvature of the minimiser K3, one CTA per point, histosys block on
+    DMMA) against hf_hessian (central differences of the analytic gradient): exact mode on the
+    data, Fisher mode on the Asimov data of each point; points inside, beyond |alpha| = 1, and with
+    the POI exactly on its bound 0."""
+    from pyhf_b200.batched import DevicePlan
+
+    if name == "c4":
+        pytest.importorskip("pyhf")
+    g = golden(name)
+    hp = g.host_plan()
+    plan = DevicePlan(hp, cuda)
+    data = np.asarray(g["data"], float)
+    rng = np.random.default_rng(7)
+    free = ~hp.fixed.astype(bool)
+    B = 6
+    width = np.minimum(0.05 * (hp.hi - hp.lo), 0.4)
+    pts = hp.init[None] + rng.normal(0, 1, (B, hp.n_pars)) * width[None] * free[None]
+    pts = np.clip(pts, hp.lo + 0.02, hp.hi - 0.02)
+    alpha = np.zeros(hp.n_pars, bool)
+    alpha[hp.hs_par] = True
+    alpha[hp.sf_par[hp.sf_kind != 0]] = True
+    pts[1, alpha & free] = 1.3       # extrapolation branches
+    pts[2, alpha & free] = -1.6
+    pts[3, hp.poi_index] = 0.0       # POI on its bound: one-sided differences in the reference matrix
+    pts[:, ~free] = hp.init[~free]
+    if name == "empty_signal_bin":
+        pts[3, hp.poi_index] = 0.3   # (lambda = 0 under n = 0 at mu = 0: the curvature of that bin is 0/0)
+    kinked = hp.hs_code == 0 or (hp.sf_kind == 2).any()
+    if kinked:                       # stay off the kink at alpha == 0 (the differences straddle it)
+        pts[:, alpha & free] = np.where(np.abs(pts[:, alpha & free]) < 0.05, 0.2, pts[:, alpha & free])
+    from oracle import hf_oracle as O
+
+    op = g.oracle_plan()
+    H_fd = plan.hessian(pts, data).cpu().numpy()
+    H_an = plan.hessian(pts, data, method="analytic").cpu().numpy()
+    asimov = plan.expected_data(pts)
+    F_fd = plan.hessian(pts, asimov).cpu().numpy()
+    F_an = plan.hessian(pts, data, method="fisher").cpu().numpy()
+    fx = ~free
+    for got, fd, what in ((H_an, H_fd, "exact"), (F_an, F_fd, "fisher")):
+        for k in range(B):
+            assert np.isfinite(got[k]).all(), (name, what, k)
+            assert np.array_equal(got[k], got[k].T)
+            # (a) the numpy closed form of the oracle (log-derivative formulation, pinned against
+            #     differences of the oracle gradient to 1e-10 in tests/test_oracle_hessian.py)
+            want = O.hessian_2nll(op, pts[k], data, what)
+            want[fx, :] = 0.0
+            want[:, fx] = 0.0
+            want[fx, fx] = 1.0
+            d = np.sqrt(np.abs(np.diag(want))) + 1e-12
+            err = np.abs(got[k] - want) / np.outer(d, d)
+            assert err.max() < 1e-9, (name, what, k, err.max(), np.unravel_index(err.argmax(), err.shape))
+            # (b) central differences of the CUDA gradient (h = 1e-4: truncation ~1e-5 where third
+            #     derivatives are large, one-sided at the POI bound)
+            d = np.sqrt(np.abs(np.diag(fd[k]))) + 1e-12
+            err = np.abs(got[k] - fd[k]) / np.outer(d, d)
+            assert err.max() < (1e-3 if k == 3 else 2e-4), (name, what, k, err.max())
+    # the Fisher matrix is positive semi-definite
+    for k in range(B):
+        w = np.linalg.eigvalsh(F_an[k][np.ix_(free, free)])
+        assert w.min() > -1e-8 * max(1.0, w.max())
+
+
 def test_counting_experiment_uncertainty_closed_form(cuda):
     """n ~ Pois(mu s + b): sigma_mu = sqrt(n) / s at the minimum"""
     from pyhf_b200.batched import DevicePlan

@@ -50,5 +50,12 @@ def test_random_spec_on_the_device(seed, cuda):
     assert int(res.status[0]) == 0
     xf = res.x[0].cpu().numpy()
     assert abs(float(res.fun[0]) - float(O.twice_nll(op, xf, data)[0])) < 1e-9 * max(1.0, abs(float(res.fun[0])))
-    _, f_cpu = O.fit(op, data)
-    assert float(res.fun[0]) <= f_cpu + 1e-6
+    # first-order optimality of the returned point (oracle gradient, projected on the bounds)
+    gr = -2.0 * O.logpdf_grad(op, xf, data)[1][0]
+    pg = np.where(free & ~((xf <= hp.lo + 1e-12) & (gr > 0)) & ~((xf >= hp.hi - 1e-12) & (gr < 0)), gr, 0.0)
+    assert np.abs(pg).max() < 1e-4, (np.abs(pg).max(), int(np.argmax(np.abs(pg))))
+    if settings is None:
+        # smooth interpolation codes: no tight CPU fit finds a lower minimum (code0 / code1 likelihoods
+        # have a kink at alpha == 0 with a local minimum on either side of it)
+        _, f_cpu = O.fit(op, data)
+        assert float(res.fun[0]) <= f_cpu + 1e-6

@@ -60,8 +60,9 @@ def test_batched_test_statistics_match_the_reference(model, stat, mode, mu, ts_g
     q = out["q"].cpu().numpy()
     ref = z[f"{model}__{stat}"]
     # both zeroing branches are present in the reference values (so the comparison means something)
+    # (q0 with the POI bounded at 0: muhat sits ON the bound, is not < 0, and q0 = fixed - free ~ 1e-13)
     if mode in ("q", "qtilde", "q0"):
-        assert (ref == 0.0).any() and (ref > 0.0).any()
+        assert (ref < 1e-9).any() and (ref > 1e-3).any()
     assert np.abs(q - ref).max() < 1e-6, (stat, q, ref)
     muhat = out["muhat"].cpu().numpy()
     assert np.abs(muhat - z[f"{model}__{stat}_muhat"]).max() < 2e-4
