@@ -321,6 +321,8 @@ void hf_plan_destroy(hf_plan* plan) {
     if (plan->h_counters) cudaFreeHost(plan->h_counters);
     cudaFree(plan->fit_block);
     cudaFree(plan->hess_block);
+    cudaFree(plan->solo_dev);
+    cudaFree(plan->solo_scratch);
     cudaFree(plan->stage_block);
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
     if (plan->s_in) cudaStreamDestroy(plan->s_in);

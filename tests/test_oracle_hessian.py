@@ -65,3 +65,40 @@ def test_multiplicative_parameter_on_zero():
     assert np.isfinite(H0).all()
     d = np.sqrt(np.abs(np.diag(H1))) + 1e-12
     assert (np.abs(H0 - H1) / np.outer(d, d)).max() < 1e-7
+
+
+def test_several_histosys_on_one_sample():
+    """C4's structure in small: every background sample carries three histosys (additive deltas:
+    the mixed second derivative of a rate in two of them is zero) next to normsys and staterror."""
+    from pyhf_b200 import synth
+    from pyhf_b200.compile import compile_spec
+
+    hp = compile_spec(synth.synth_spec(2, 4, 2, 3, 2, 1, seed=5), poi_name="mu")
+    op = O.Plan(hp.arrays())
+    rng = np.random.default_rng(3)
+    data = O.expected_data(op, hp.init[None])[0]
+    data[: hp.n_bins] = rng.poisson(data[: hp.n_bins])
+    free = ~hp.fixed.astype(bool)
+    for trial in range(2):
+        x = np.clip(hp.init + rng.normal(0, 0.3, hp.n_pars) * free, hp.lo + 0.02, hp.hi - 0.02)
+        for mode in ("exact", "fisher"):
+            d = data if mode == "exact" else O.expected_data(op, x[None])[0]
+            want = _fd_hessian(op, x, d)
+            got = O.hessian_2nll(op, x, data, mode)
+            dd = np.sqrt(np.abs(np.diag(want))) + 1e-12
+            err = (np.abs(got - want) / np.outer(dd, dd))[np.ix_(free, free)]
+            assert err.max() < 1e-8, (trial, mode, err.max())
+
+
+def test_histosys_delta_cancelling_the_nominal():
+    """base = nominal + delta exactly 0 in one cell (the reference's coupled-histosys validation model
+    at alpha = -1.6): the closed form stays finite"""
+    from conftest import Golden, GOLDEN
+    import os
+
+    g = Golden(os.path.join(GOLDEN, "val_2bin_2channel_coupledhistosys.npz"))
+    op, hp = g.oracle_plan(), g.host_plan()
+    x = hp.init.copy()
+    x[hp.hs_par] = -1.6
+    H = O.hessian_2nll(op, x, np.asarray(g["data"], float))
+    assert np.isfinite(H).all()
