@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["hf_abi.cu", "hf_eval.cu", "hf_eval_mma.cu", "hf_fit.cu", "hf_fit_solo.cu", "hf_hess.cu", "hf_hess_analytic.cu", "hf_toys.cu"]
+SOURCES = ["hf_abi.cu", "hf_eval.cu", "hf_eval_mma.cu", "hf_fit.cu", "hf_fit_solo.cu", "hf_fit_solo128.cu", "hf_hess.cu", "hf_hess_analytic.cu", "hf_toys.cu"]
 LIB = os.path.join(HERE, "libhf_b200.so")
 
 NVCC_FLAGS = [

@@ -258,6 +258,7 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
             bl_mask.insert(bl_mask.end(), mk.begin(), mk.end());
         }
     }
+    for (int c = 0; c < NSEG; ++c) plan->ah_max_lc = std::max(plan->ah_max_lc, bl_ptr[seg_first[c + 1]] - bl_ptr[seg_first[c]]);
     const size_t o_ahl = pk.add(sfp_list.data(), sizeof(int32_t) * sfp_list.size());
     const size_t o_ahj = pk.add(sf_j.data(), sizeof(int32_t) * NSF);
     const size_t o_ahbp = pk.add(bl_ptr.data(), sizeof(int32_t) * (NB + 1));
