@@ -272,7 +272,8 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- M2 on the host cores
 def c3_inputs():
-    """config 3: C3 plan + observed data (one draw at suggested_init under np.random.seed(0))"""
+    """config 3: C3 plan + observed data: one background-only draw (POI = 0, every other parameter at
+    suggested_init) under np.random.seed(0), so that the mu = 1 hypothesis is actually tested (qobs > 0)"""
     from pyhf_b200 import synth
 
     try:
@@ -284,14 +285,20 @@ def c3_inputs():
         model = pyhf.Model(synth.spec_c3(), poi_name="mu", validate=False)
         hp = extract_plan(model)
         np.random.seed(0)
-        data = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(hp.init)).sample((1,))[0], dtype=np.float64)
+        bkg = np.array(hp.init, dtype=np.float64)
+        bkg[hp.poi_index] = 0.0
+        data = np.asarray(model.make_pdf(pyhf.tensorlib.astensor(bkg)).sample((1,))[0], dtype=np.float64)
     except ImportError:
         from pyhf_b200.compile import compile_spec
 
         hp = compile_spec(synth.spec_c3(), poi_name="mu")
         rng = np.random.default_rng(0)
         data = np.empty(hp.n_data)
-        data[: hp.n_bins] = rng.poisson(hp.nominal.sum(axis=0))
+        # background-only expectation: leave out the samples the POI scales (q = sample * n_segs + segment)
+        sig = {q // hp.n_segs for q in range(hp.n_samples * hp.n_segs)
+               if hp.poi_index in hp.sf_par[hp.sf_ptr[q]:hp.sf_ptr[q + 1]]}
+        keep = [i for i in range(hp.n_samples) if i not in sig]
+        data[: hp.n_bins] = rng.poisson(hp.nominal[keep].sum(axis=0))
         data[hp.n_bins + hp.g_aux] = rng.normal(hp.auxdata[hp.g_aux], hp.g_sigma)
         data[hp.n_bins + hp.p_aux] = rng.poisson(hp.p_factor)
     return hp, data
@@ -592,6 +599,14 @@ def toy_hypotest_legs(args, batched, c4_plan, c4_data, rank, world, barrier, dis
     legs["toy_fits"] = {"metric": "q~ toy fits/s per GPU (C3: 100 bins, 120 parameters), rank 0", "value": 2 * count / dt,
                         "unit": "fits/s", "ntoys": count, "failed_fits": int((st != 0).sum()),
                         "mean_newton_iterations": float(out["free"].niter.float().mean())}
+    try:
+        fk = plan3.fit_kernel_info()
+        legs["toy_fits"]["fit_kernel"] = fk
+        legs["toy_fits"]["occupancy"] = fk.get("occupancy_theoretical")
+        legs["toy_fits"]["occupancy_note"] = ("resident warps / 64 per SM from the launch shape; the achieved figure of "
+                                              "the same kernel under ncu is in profiles/ (sm__warps_active)")
+    except Exception as exc:
+        legs["toy_fits"]["fit_kernel"] = {"error": repr(exc)}
     del plan3, toys, out
     torch.cuda.empty_cache()
     # ---------------- config 5 at reduced toy count: C4, toys sharded the same way

@@ -137,7 +137,7 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
  */
 typedef struct {
     int32_t max_iter;   /* default 200 */
-    int32_t history;    /* L-BFGS memory, default 8 (max 16) */
+    int32_t reserved0;  /* (unused; keeps the layout of earlier builds) */
     double tol_edm;     /* stop when the estimated 2*NLL distance to the minimum < tol_edm (default 1e-11) */
     double tol_step;    /* and the preconditioned step max-norm < tol_step (default 1e-8) */
     int32_t verbose;
@@ -171,6 +171,12 @@ int hf_fit_batch_masks(hf_plan* plan, const double* data, int64_t data_rows, con
                        const uint8_t* masks, int32_t n_masks, const uint8_t* mask_id, int64_t N,
                        const hf_fit_opts* opts, double* x, double* fun, int32_t* status,
                        int32_t* niter, void* stream);
+/* Launch shape of the most recent hf_fit_* call on this plan (bench.py reports it next to fits/s):
+ * info[0] = 1 per-fit kernel (one CTA per fit, hf_fit_solo.cu) / 0 lock-step driver (hf_fit.cu),
+ * [1] grid (persistent CTAs), [2] threads per CTA, [3] resident CTAs per SM, [4] dynamic shared memory
+ * per CTA (bytes), [5] SMs of the device, [6] 1 when the per-bin block is eliminated in low-rank form,
+ * [7] reserved. */
+int hf_plan_fit_info(const hf_plan* plan, int32_t info[8]);
 int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,
                       const double* init_host, int64_t init_rows, const double* lo_host,
                       const double* hi_host, const uint8_t* fixed_host, int64_t N,

@@ -35,7 +35,7 @@ class FitOpts(C.Structure):
     """mirror of ``hf_fit_opts``"""
 
     _fields_ = [
-        ("max_iter", C.c_int32), ("history", C.c_int32), ("tol_edm", C.c_double),
+        ("max_iter", C.c_int32), ("reserved0", C.c_int32), ("tol_edm", C.c_double),
         ("tol_step", C.c_double), ("verbose", C.c_int32), ("reserved", C.c_int32),
     ]
 
@@ -51,6 +51,7 @@ SIGNATURES = {
     "hf_plan_launch_count": (_i64, [_vp]),
     "hf_plan_set_timing": (C.c_int, [_vp, C.c_int]),
     "hf_plan_main_kernel_ms": (C.c_int, [_vp, c_dp, C.POINTER(C.c_int64)]),
+    "hf_plan_fit_info": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "hf_logpdf": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "hf_logpdf_grad": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hf_expected_data": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

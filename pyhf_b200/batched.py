@@ -317,6 +317,22 @@ class DevicePlan:
     def launch_count(self):
         return int(self._lib.hf_plan_launch_count(self._h))
 
+    def fit_kernel_info(self):
+        """launch shape of the most recent fit batch on this plan (hf_plan_fit_info): which form of
+        K3 ran, persistent grid, CTA size, resident CTAs per SM, shared memory per CTA and the
+        theoretical occupancy that follows (resident warps / 64 per SM)"""
+        info = (C.c_int32 * 8)()
+        _lib.check(self._lib.hf_plan_fit_info(self._h, info))
+        solo = bool(info[0])
+        out = {"form": "per-fit kernel (one CTA per fit, hf_fit_solo.cu)" if solo
+               else "lock-step driver (hf_fit.cu: one batched K2 launch per round)"}
+        if solo:
+            out.update(grid=int(info[1]), threads_per_cta=int(info[2]), ctas_per_sm=int(info[3]),
+                       smem_bytes_per_cta=int(info[4]), sms=int(info[5]),
+                       low_rank_per_bin_block=bool(info[6]),
+                       occupancy_theoretical=info[2] * info[3] / 2048.0)
+        return out
+
     def set_timing(self, enable=True):
         """bracket every launch of the dominant kernel with CUDA events (bench.py roofline)"""
         _lib.check(self._lib.hf_plan_set_timing(self._h, int(bool(enable))))

@@ -545,11 +545,22 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
 void hf_fit_default_opts(hf_fit_opts* o) {
     if (!o) return;
     o->max_iter = 200;
-    o->history = 8;
+    o->reserved0 = 0;
     o->tol_edm = 1e-11;
     o->tol_step = 1e-8;
     o->verbose = 0;
     o->reserved = 0;
+}
+
+int hf_plan_fit_info(const hf_plan* plan, int32_t info[8]) {
+    if (!plan || !info) {
+        hf_set_error("hf_plan_fit_info: null argument");
+        return HF_ERR_INVALID;
+    }
+    info[0] = plan->solo_last_nt > 0 ? 1 : 0;
+    info[1] = plan->solo_last_grid; info[2] = plan->solo_last_nt; info[3] = plan->solo_last_occ;
+    info[4] = plan->solo_last_smem; info[5] = plan->sm_count; info[6] = plan->solo_last_lowrank; info[7] = 0;
+    return HF_OK;
 }
 
 int hf_fit_batch(hf_plan* plan, const double* data, int64_t data_rows, const double* init,

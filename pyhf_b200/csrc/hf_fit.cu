@@ -49,6 +49,7 @@ struct FitDev {
     int* nindef;                // consecutive near-stationary directions (edm < 1e-3) whose Hessian needed a shift
     int* chk;                   // the stopping rule is being re-checked without damping at this point
     int* hfresh;                // the fit's matrix is the exact Hessian AT its current point
+    double* kscale;             // relative size of the next saddle kick (shrinks when a kick lands outside the domain)
     double* damp;                 // Levenberg-Marquardt damping added to the diagonal (0 = pure Newton)
     int *live, *live_next;   // compacted list of fits still running (order is arbitrary)
     const int* islocal;      // [P] 1 when the parameter only couples to the global block (diagonal local block)
@@ -104,7 +105,7 @@ __global__ void fit_init_kernel(FitDev s, const double* __restrict__ init, int64
         s.done[i] = 0; s.need_dir[i] = 1; s.own[i] = 0; s.status[i] = 1; s.niter[i] = 0;
         s.refresh[i] = 0; s.T[i] = 1.0; s.EDM[i] = INFINITY; s.EDMPREV[i] = INFINITY;
         s.nfail[i] = 0; s.force[i] = 0; s.damp[i] = s.damp0; s.pending[i] = 0;
-        s.indef[i] = 0; s.nkick[i] = 0; s.kick[i] = 0; s.nindef[i] = 0; s.chk[i] = 0; s.hfresh[i] = 0;
+        s.indef[i] = 0; s.nkick[i] = 0; s.kick[i] = 0; s.nindef[i] = 0; s.chk[i] = 0; s.hfresh[i] = 0; s.kscale[i] = 1e-3;
     }
 }
 
@@ -275,7 +276,7 @@ __device__ void fit_write_kick(const FitDev& s, int64_t toy, int tid, int nth) {
     for (int p = tid; p < P; p += nth) {
         const unsigned hsh = ((unsigned)(p + 1) * 2654435761u + salt) >> 8;
         const double u = (double)(hsh & 0xffffu) / 32768.0 - 1.0;
-        d[p] = mask[p] ? 0.0 : 1e-3 * fmax(1.0, fabs(x[p])) * u;
+        d[p] = mask[p] ? 0.0 : s.kscale[toy] * fmax(1.0, fabs(x[p])) * u;
     }
     __syncthreads();
     if (tid == 0) {
@@ -813,10 +814,23 @@ __global__ void fit_accept_kernel(FitDev s, const int* __restrict__ live, int64_
     const double ft = -2.0 * VTc[k];
     const double slack = 4e-15 * fmax(1.0, fabs(f));
     const bool kicked = s.kick[toy] == 1;  // displaced off a saddle: taken unconditionally
-    const bool ok = isfinite(ft) && (kicked || ft <= f + kArmijo * dec + slack);
+    // a kick is taken unconditionally as long as it stays inside the domain and costs less than one unit
+    // of 2NLL; else it is tried again at a tenth of the size (narrow valleys: curvatures of 1e7 and a
+    // clipped rate next to the saddle in the reference's clipping model)
+    const bool ok = isfinite(ft) && (kicked ? ft <= f + 1.0 : ft <= f + kArmijo * dec + slack);
     bool alive = true;
-    if (kicked && !ok) {  // (not even finite: stay where the fit was)
-        if (lane == 0) { s.done[toy] = 1; s.status[toy] = 0; s.kick[toy] = 0; }
+    if (kicked && !ok) {
+        if (lane == 0) {
+            if (s.kscale[toy] > 1e-9) {
+                s.kscale[toy] *= 0.1;
+                s.kick[toy] = 2;
+                s.need_dir[toy] = 1;
+                s.nkick[toy] -= 1;
+                live_next[atomicAdd(&s.counters[1], 1)] = (int)toy;
+            } else {  // stay where the fit was
+                s.done[toy] = 1; s.status[toy] = 0; s.kick[toy] = 0;
+            }
+        }
         return;
     }
     if (s.trace && (nl <= 3 || toy < 2) && lane == 0)
@@ -975,6 +989,32 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     const int P = plan->P, D = plan->D;
     build_fd_structure(plan);
 
+    plan->solo_last_nt = 0;  // (set again by the per-fit kernel when it takes the batch)
+    // plans inside the scope of the per-fit kernel run there: one CTA per fit, no host in the loop
+    // (hf_fit_solo.cu); everything else takes the lock-step driver below
+    if (hf_fit_solo_supported(plan)) {
+        double* DC = nullptr;
+        const size_t need_dc = sizeof(double) * (size_t)data_rows + 256;
+        if (need_dc > plan->fit_bytes) {
+            if (plan->fit_block) cudaFree(plan->fit_block);
+            plan->fit_block = nullptr;
+            plan->fit_bytes = 0;
+            cudaError_t e = cudaMalloc(&plan->fit_block, need_dc);
+            if (e != cudaSuccess) {
+                hf_set_error("cudaMalloc(%zu) for the fit workspace: %s", need_dc, cudaGetErrorString(e));
+                return HF_ERR_NOMEM;
+            }
+            plan->fit_bytes = need_dc;
+        }
+        DC = reinterpret_cast<double*>(plan->fit_block);
+        int rc0 = hf_data_const_launch(plan, data, data_rows, DC, st);
+        if (rc0) return rc0;
+        int handled = 0;
+        rc0 = hf_fit_solo_launch(plan, data, data_rows, DC, init, init_rows, lo, hi, fixed, fixed_alt, use_alt, n_alt,
+                                 data_map, N, opts, x_out, fun_out, status_out, niter_out, st, &handled);
+        if (rc0) return rc0;
+        if (handled) return HF_OK;
+    }
     // ---- column structure for this fixed mask (host: P is small)
     // (a parameter gets no FD column only when it is fixed under every mask of the batch)
     std::vector<uint8_t> h_fixed(P), h_alt;
@@ -1001,31 +1041,6 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
     int nfree = 0;
     for (int p = 0; p < P; ++p) nfree += h_fixed[p] ? 0 : 1;
 
-    // plans inside the scope of the per-fit kernel run there: one CTA per fit, no host in the loop
-    // (hf_fit_solo.cu); everything else takes the lock-step driver below
-    if (hf_fit_solo_supported(plan)) {
-        double* DC = nullptr;
-        const size_t need_dc = sizeof(double) * (size_t)data_rows + 256;
-        if (need_dc > plan->fit_bytes) {
-            if (plan->fit_block) cudaFree(plan->fit_block);
-            plan->fit_block = nullptr;
-            plan->fit_bytes = 0;
-            cudaError_t e = cudaMalloc(&plan->fit_block, need_dc);
-            if (e != cudaSuccess) {
-                hf_set_error("cudaMalloc(%zu) for the fit workspace: %s", need_dc, cudaGetErrorString(e));
-                return HF_ERR_NOMEM;
-            }
-            plan->fit_bytes = need_dc;
-        }
-        DC = reinterpret_cast<double*>(plan->fit_block);
-        int rc0 = hf_data_const_launch(plan, data, data_rows, DC, st);
-        if (rc0) return rc0;
-        int handled = 0;
-        rc0 = hf_fit_solo_launch(plan, data, data_rows, DC, init, init_rows, lo, hi, fixed, fixed_alt, use_alt, n_alt,
-                                 data_map, N, opts, x_out, fun_out, status_out, niter_out, st, &handled);
-        if (rc0) return rc0;
-        if (handled) return HF_OK;
-    }
     // curvature: closed form (hf_hess_analytic.cu) when the plan qualifies, else forward differences
     // of the analytic gradient
     bool use_ah = plan->d.ah_ok != 0;
@@ -1070,6 +1085,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
         s.nindef = c.take<int>(NC);
         s.chk = c.take<int>(NC);
         s.hfresh = c.take<int>(NC);
+        s.kscale = c.take<double>(NC);
         s.damp = c.take<double>(NC);
         AHS = use_ah ? c.take<double>((size_t)ah_cap * ah_stride) : nullptr;
         d_islocal = c.take<int>(P);

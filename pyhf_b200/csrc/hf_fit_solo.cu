@@ -237,6 +237,7 @@ int hf_fit_solo_launch(hf_plan* plan, const double* data, int64_t data_rows, con
     plan->solo_last_occ = occ;
     plan->solo_last_smem = (int)smem;
     plan->solo_last_nt = NT;
+    plan->solo_last_lowrank = L.lowrank;
     *handled = 1;
     return HF_OK;
 }

@@ -1059,7 +1059,7 @@ fit_solo_kernel(DevPlan pl, SoloArgs a) {
         __syncthreads();
         double f = INFINITY;
         int status = 1, niter = 0, nfail = 0, nkick = 0, nindef = 0;
-        double damp = a.damp0, edm_prev = INFINITY;
+        double damp = a.damp0, edm_prev = INFINITY, kscale = 1e-3;
         bool kick_next = false, chk = false, exact_tried = false;
         bool need_sweep = true;  // value, gradient and Hessian of the current point are due (ONE call site: the sweep is inlined)
         const int max_rounds = a.max_iter * 4 + 40;
@@ -1080,7 +1080,7 @@ fit_solo_kernel(DevPlan pl, SoloArgs a) {
                 for (int p = tid; p < P; p += NT) {
                     const unsigned hsh = ((unsigned)(p + 1) * 2654435761u + salt) >> 8;
                     const double u = (double)(hsh & 0xffffu) / 32768.0 - 1.0;
-                    c.d[p] = mask[p] ? 0.0 : 1e-3 * fmax(1.0, fabs(c.xc[p])) * u;
+                    c.d[p] = mask[p] ? 0.0 : kscale * fmax(1.0, fabs(c.xc[p])) * u;
                 }
                 __syncthreads();
                 kick_next = false;
@@ -1132,12 +1132,18 @@ fit_solo_kernel(DevPlan pl, SoloArgs a) {
             for (int p = tid; p < P; p += NT) dec = fma(c.g[p], c.xt[p] - c.xc[p], dec);
             dec = block_sum(dec, c.red);
             const double slack = 4e-15 * fmax(1.0, fabs(f));
-            const bool ok = isfinite(ft) && (kicked || ft <= f + kArmijo * dec + slack);
+            // (a kick is taken unconditionally as long as it stays inside the domain and costs less than one
+            //  unit of 2NLL; else it is tried again at a tenth of the size)
+            const bool ok = isfinite(ft) && (kicked ? ft <= f + 1.0 : ft <= f + kArmijo * dec + slack);
             if (((a.trace && fit < 2) || fit == a.trace_fit) && tid == 0)
                 printf("[hf_fit solo] fit %lld it %d f %.12g ft-f %.3e dec %.3e edm %.3e step %.3e damp %.3e %s attempts %d %s\n",
                        (long long)fit, niter, f, ft - f, dec, edm, step, damp, fisher ? "fisher" : "exact", attempts,
                        ok ? "accept" : "reject");
-            if (kicked && !ok) { status = 0; break; }  // (not even finite: stay where the fit was)
+            if (kicked && !ok) {
+                if (kscale > 1e-9) { kscale *= 0.1; kick_next = true; nkick -= 1; continue; }
+                status = 0;  // stay where the fit was
+                break;
+            }
             if (ok) {
                 __syncthreads();
                 for (int p = tid; p < P; p += NT) c.xc[p] = c.xt[p];

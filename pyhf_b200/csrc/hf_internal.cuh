@@ -267,7 +267,7 @@ struct hf_plan {
     int ah_max_lc = 0;  // most (bin, per-bin parameter) pairs inside one segment
     void* solo_scratch = nullptr;
     size_t solo_scratch_bytes = 0;
-    int solo_last_grid = 0, solo_last_occ = 0, solo_last_smem = 0, solo_last_nt = 0;  // launch shape of the last batch (bench.py)
+    int solo_last_grid = 0, solo_last_occ = 0, solo_last_smem = 0, solo_last_nt = 0, solo_last_lowrank = 0;  // launch shape of the last batch (bench.py)
     // workspace of hf_hessian
     void* hess_block = nullptr;
     size_t hess_bytes = 0;
