@@ -356,6 +356,25 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the b200 path has no CPU fallback)")
     torch.cuda.set_device(local)
+    # pin this rank to the CPU cores (NUMA node) next to its GPU BEFORE any pinned host buffer is
+    # allocated: first-touch then places the staging memory on the socket the GPU hangs off, and the
+    # host <-> device copies of 8 ranks do not cross the inter-socket link
+    affinity = "unchanged"
+    if world > 1:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(local)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+            cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu]
+            allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                affinity = f"{len(allowed)} cores next to GPU {local} (NVML cpu affinity): {allowed[0]}-{allowed[-1]}"
+        except Exception as exc:  # not fatal: the run is then as the launcher placed it
+            affinity = f"unchanged ({exc!r})"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -424,6 +443,8 @@ def run_b200(args):
     grad_h = torch.empty(B, hp.n_pars, dtype=torch.float64).pin_memory()
     plan.logpdf_grad_host(pars_h, data_h, out_h, grad_h)
     e2e_steps = max(3, min(args.steps, 10))
+    h2d_bytes = int(pars_h.numel() * 8 + data_h.numel() * 8)
+    d2h_bytes = int(grad_h.numel() * 8 + out_h.numel() * 8)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -433,13 +454,28 @@ def run_b200(args):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(te[0])
+    e2e_ms = 1e3 * float(te[0]) / e2e_steps
+
+    # ---- where the end-to-end time goes: each direction of the host link alone, all ranks at once
+    def copy_only(fn, reps=5):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return 1e3 * float(tt[0]) / reps
+
+    h2d_ms = copy_only(lambda: pars.copy_(pars_h, non_blocking=True))
+    d2h_ms = copy_only(lambda: grad_h.copy_(grad, non_blocking=True))
     # the device-resident result and the host-buffer result are the same numbers
     assert torch.allclose(out_h, out.cpu(), rtol=1e-12, atol=0, equal_nan=True)
 
     # ---- the north star's second metric, at every N: toy-based hypotests sharded over the ranks
     toy_legs = {}
-    h2d_bytes = int(pars_h.numel() * 8 + data_h.numel() * 8)
-    d2h_bytes = int(grad_h.numel() * 8 + out_h.numel() * 8)
     if not args.no_toys:
         del pars, grad, out, pars_h, grad_h, out_h
         torch.cuda.empty_cache()
@@ -483,11 +519,18 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "batch_per_gpu": B, "parallelism": f"{world} independent shards (no collective)",
-                   "l2": "inputs larger than L2 (pars 157 MB + grad 157 MB per step)"},
+                   "l2": "inputs larger than L2 (pars 157 MB + grad 157 MB per step)",
+                   "rank0_cpu_affinity": affinity},
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "path": "hf_logpdf_grad_host (C-ABI, pinned host buffers)"},
+                "path": "hf_logpdf_grad_host (C-ABI, pinned host buffers)",
+                "ms_per_step": e2e_ms,
+                "breakdown_ms_per_step": {
+                    "h2d_only": h2d_ms, "d2h_only": d2h_ms, "kernels_only": ms_max / args.steps,
+                    "note": "each leg timed alone with all ranks active at once (max over ranks); the host-buffer "
+                            "call pipelines the three over wave-aligned chunks, so its floor is the slowest leg",
+                    "h2d_gbs_per_rank": h2d_bytes / h2d_ms / 1e6, "d2h_gbs_per_rank": d2h_bytes / d2h_ms / 1e6}},
         "roofline": roofline,
     }
 

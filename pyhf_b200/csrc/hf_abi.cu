@@ -427,6 +427,7 @@ extern "C" {
 
 int hf_logpdf(hf_plan* plan, const double* pars, const double* data, int64_t data_rows, int64_t B,
               double* out, void* stream) {
+    HfRange nvtx_range("K1 hf_logpdf");
     if (!plan || !pars || !data || !out) {
         hf_set_error("null argument");
         return HF_ERR_INVALID;
@@ -436,6 +437,7 @@ int hf_logpdf(hf_plan* plan, const double* pars, const double* data, int64_t dat
 
 int hf_logpdf_grad(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
                    int64_t B, double* out, double* grad, void* stream) {
+    HfRange nvtx_range("K2 hf_logpdf_grad");
     if (!plan || !pars || !data || !out || !grad) {
         hf_set_error("null argument");
         return HF_ERR_INVALID;
@@ -444,6 +446,7 @@ int hf_logpdf_grad(hf_plan* plan, const double* pars, const double* data, int64_
 }
 
 int hf_expected_data(hf_plan* plan, const double* pars, int64_t B, double* out, void* stream) {
+    HfRange nvtx_range("hf_expected_data");
     if (!plan || !pars || !out) {
         hf_set_error("null argument");
         return HF_ERR_INVALID;
@@ -454,6 +457,7 @@ int hf_expected_data(hf_plan* plan, const double* pars, int64_t B, double* out, 
 int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* data_host,
                         int64_t data_rows, int64_t B, double* out_host, double* grad_host,
                         void* stream) {
+    HfRange nvtx_range("K2 hf_logpdf_grad_host");
     if (!plan || !pars_host || !data_host || !out_host) {
         hf_set_error("null argument");
         return HF_ERR_INVALID;
@@ -653,6 +657,7 @@ int hf_fit_batch_host(hf_plan* plan, const double* data_host, int64_t data_rows,
 
 int hf_sample_toys(hf_plan* plan, const double* pars, uint64_t seed, uint64_t offset, int64_t N,
                    double* out, void* stream) {
+    HfRange nvtx_range("K4 hf_sample_toys");
     if (!plan || !pars || !out) {
         hf_set_error("null argument");
         return HF_ERR_INVALID;

@@ -969,6 +969,7 @@ int hf_fit_launch(hf_plan* plan, const double* data, int64_t data_rows, const do
                   int64_t N, const hf_fit_opts* opts_in, double* x_out, double* fun_out,
                   int32_t* status_out, int32_t* niter_out, cudaStream_t st,
                   const uint8_t* fixed_alt, const uint8_t* use_alt, const int32_t* data_map, int n_alt) {
+    HfRange nvtx_range("K3 hf_fit_batch");
     if (N <= 0) return HF_OK;
     if (n_alt < 1 || n_alt > 255) {
         hf_set_error("the mask table holds 1..255 alternative masks (got %d)", n_alt);

@@ -70,6 +70,7 @@ __global__ void hess_assemble_kernel(int P, int64_t nb, const double* __restrict
 extern "C" int hf_hessian(hf_plan* plan, const double* pars, const double* data, int64_t data_rows,
                           int64_t B, const double* lo, const double* hi, const uint8_t* fixed,
                           double* hess, void* stream) {
+    HfRange nvtx_range("hf_hessian");
     if (!plan || !pars || !data || !lo || !hi || !fixed || !hess) {
         hf_set_error("null argument");
         return HF_ERR_INVALID;

@@ -232,6 +232,15 @@ __host__ __device__ inline double hf_pois_term(double n, double lam) {
 }
 
 // ---------------------------------------------------------------- host-side helpers
+// NVTX range around a C-ABI entry point (K1..K5 of DESIGN.md): shows up in Nsight timelines and
+// lets `ncu --nvtx --nvtx-include` select the kernels of one path
+#include <nvtx3/nvToolsExt.h>
+struct HfRange {
+    explicit HfRange(const char* name) { nvtxRangePushA(name); }
+    ~HfRange() { nvtxRangePop(); }
+    HfRange(const HfRange&) = delete;
+    HfRange& operator=(const HfRange&) = delete;
+};
 void hf_set_error(const char* fmt, ...);
 #define HF_CUDA_OK(call)                                                              \
     do {                                                                              \

@@ -276,6 +276,7 @@ int hf_sample_normal(const double* loc, const double* scale, int64_t M, int64_t 
 
 int hf_teststat(const double* fun_fixed, const double* fun_free, const double* muhat, double mu,
                 int32_t mode, int64_t N, double* q, void* stream) {
+    HfRange nvtx_range("K5 hf_teststat");
     if (!fun_fixed || !fun_free || !muhat || !q) {
         hf_set_error("null argument");
         return HF_ERR_INVALID;

@@ -80,6 +80,13 @@ class B200Optimizer:
         return key, matrix, int(row), base
 
     def _fit(self, plan, data, init, lo, hi, fixed, opts):
+        # ``tolerance``: the reference hands it to scipy as ``tol`` (optimize/opt_scipy.py:96-105), which
+        # SLSQP reads as ftol -- stop when 2NLL changes by less than that between two iterates.  The
+        # Newton iteration here stops on the same quantity, predicted instead of observed: the
+        # estimated distance of 2NLL to the minimum (``tol_edm``, and a step below 1e-8).  So an
+        # explicit tolerance keeps its meaning; only the DEFAULT differs on purpose (1e-11 instead
+        # of scipy's 1e-6, which leaves the reference 1e-5 .. 0.5 above the minimum in 2NLL and
+        # cannot meet the 1e-6 bar on q~ / CLs).
         tol = opts.get("tolerance", self.tolerance)
         kw = {"max_iter": opts.get("maxiter", self.maxiter), "verbose": opts.get("verbose", self.verbose)}
         if tol is not None:
