@@ -38,7 +38,7 @@ class _Result(dict):
 class B200Optimizer:
     """Batched on-device minimiser behind pyhf's optimizer socket."""
 
-    __slots__ = ["name", "maxiter", "verbose", "tolerance", "_cache", "_stats", "__weakref__"]
+    __slots__ = ["name", "maxiter", "verbose", "tolerance", "_cache", "_stats", "_consts", "__weakref__"]
 
     def __init__(self, *args, **kwargs):
         # reference: optimize/mixins.py:19-32 (unknown kwargs -> Unsupported)
@@ -51,6 +51,7 @@ class B200Optimizer:
 
             raise pyhf.exceptions.Unsupported(f"Unsupported kwargs were passed in: {list(kwargs)}.")
         self._cache = {}
+        self._consts = {}
         self._stats = {"batched_fits": 0, "cache_hits": 0, "single_fits": 0}
 
     # ------------------------------------------------------------------ helpers
@@ -91,7 +92,19 @@ class B200Optimizer:
         kw = {"max_iter": opts.get("maxiter", self.maxiter), "verbose": opts.get("verbose", self.verbose)}
         if tol is not None:
             kw["tol_edm"] = float(tol)
+        # bounds and masks repeat from call to call (five fits per hypotest, one call per toy): their
+        # device copies are kept, so a fit uploads its start point and data only
+        lo, hi, fixed = (self._on_device(plan, a) for a in (lo, hi, fixed))
         return plan.fit(data, init, lo, hi, fixed, **kw)
+
+    def _on_device(self, plan, arr):
+        key = (id(plan), arr.dtype.str, arr.tobytes())
+        t = self._consts.get(key)
+        if t is None:
+            if len(self._consts) > 64:
+                self._consts.clear()
+            t = self._consts[key] = (torch.as_tensor(np.ascontiguousarray(arr), device=plan.device), plan)
+        return t[0]
 
     # ------------------------------------------------------------------ the plugin entry point
     def minimize(
@@ -162,7 +175,7 @@ class B200Optimizer:
             res = self._fit(plan, d, init, bounds[:, 0], bounds[:, 1], fixed, opts)
             self._stats["single_fits"] += 1
             x, fun = res.x[0], res.fun[0]
-            status, nit = int(res.status[0]), int(res.niter[0])
+            status, nit = (int(v) for v in torch.stack([res.status[0], res.niter[0]]).tolist())  # one read-back
 
         result = _Result(x=x, fun=fun, success=(status == 0), status=status, nit=nit,
                          message=("converged", "iteration limit reached", "numerical failure")[status],
