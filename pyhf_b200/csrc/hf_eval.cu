@@ -515,6 +515,150 @@ hf_main_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// point-major form of the hot kernel for plans WITHOUT histosys (C3-class models)
+// ------------------------------------------------------------------------------------------
+// hf_main_kernel maps thread = bin with a register tile of points, which is what the histosys
+// contraction wants; without histosys a (point, bin) costs ~S multiplies, one log and one divide,
+// and that mapping leaves most of a warp's work in index arithmetic and shared-memory broadcasts
+// (1.1e8 evals/s on C3, ~20 cycles per (point, bin) and SM).  Here thread = parameter point (lanes =
+// consecutive points: every access to the batch-major scratch parsT / FsegT / GsegT / gradT is
+// coalesced), a block sweeps one tile of PM_BT bins whose tables (nominal, per-bin parameter
+// indices, segment ids, shared observed counts) sit in shared memory and are read as broadcasts,
+// the scalar factors of the current segment live in registers, and the sums leave through
+// fire-and-forget fp64 reductions (RED), one per (point, quantity) and tile.
+constexpr int PM_BT = 32;    // bins per block
+constexpr int PM_TB = 128;   // points per block
+constexpr int PM_SMAX = 8;   // samples held in registers
+constexpr int PM_KMAX = 4;   // per-bin factors on one cell
+
+template <bool GRAD>
+__global__ void __launch_bounds__(PM_TB)
+hf_main_pm_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
+                  int per_point, const int* __restrict__ row_idx) {
+    __shared__ double s_nom[PM_SMAX][PM_BT];
+    __shared__ double s_data[PM_BT];
+    __shared__ int s_bf[PM_KMAX][PM_SMAX][PM_BT];
+    __shared__ int s_seg[PM_BT];
+    const int tid = threadIdx.x;
+    const int S = pl.S, K = pl.K, NB = pl.NB, NSEG = pl.NSEG;
+    const int b0 = blockIdx.y * PM_BT;
+    const int nb = min(PM_BT, NB - b0);
+    for (int i = tid; i < S * PM_BT; i += PM_TB) {
+        const int s_ = i / PM_BT, bl = i - s_ * PM_BT;
+        const int bb = min(b0 + bl, NB - 1);
+        s_nom[s_][bl] = pl.nominal[(int64_t)s_ * NB + bb];
+        for (int k = 0; k < K; ++k) s_bf[k][s_][bl] = pl.bf_par[((int64_t)k * S + s_) * NB + bb];
+    }
+    if (tid < PM_BT) {
+        const int bb = min(b0 + tid, NB - 1);
+        s_seg[tid] = pl.bin_seg[bb];
+        s_data[tid] = (!per_point && !row_idx) ? data[bb] : 0.0;
+    }
+    __syncthreads();
+    const int64_t pt = (int64_t)blockIdx.x * PM_TB + tid;
+    if (pt >= ld) return;
+    const int64_t ptc = (pt < B) ? pt : B - 1;  // padded points repeat the last one
+    const bool own_row = per_point || row_idx;
+    const double* drow = data + (row_idx ? (int64_t)row_idx[ptc] : (per_point ? ptc : 0)) * pl.D;
+
+    double F[PM_SMAX], G[PM_SMAX];
+#pragma unroll
+    for (int s_ = 0; s_ < PM_SMAX; ++s_) F[s_] = G[s_] = 0.0;
+    int cur = -1;
+    double macc = 0.0;
+    for (int bl = 0; bl < nb; ++bl) {
+        const int seg = s_seg[bl];
+        if (seg != cur) {  // (uniform across the block)
+            if (GRAD && cur >= 0) {
+#pragma unroll
+                for (int s_ = 0; s_ < PM_SMAX; ++s_)
+                    if (s_ < S) atomicAdd(&w.GsegT[((int64_t)s_ * NSEG + cur) * ld + pt], G[s_]);
+            }
+#pragma unroll
+            for (int s_ = 0; s_ < PM_SMAX; ++s_) {
+                G[s_] = 0.0;
+                if (s_ < S) F[s_] = w.FsegT[((int64_t)s_ * NSEG + seg) * ld + pt];
+            }
+            cur = seg;
+        }
+        double lam = 0.0, bfs[PM_SMAX];
+#pragma unroll
+        for (int s_ = 0; s_ < PM_SMAX; ++s_) {
+            bfs[s_] = 1.0;
+            if (s_ < S) {
+                for (int k = 0; k < K; ++k) {
+                    const int p = s_bf[k][s_][bl];
+                    if (p >= 0) bfs[s_] *= w.parsT[(int64_t)p * ld + pt];
+                }
+                double r = F[s_] * bfs[s_] * s_nom[s_][bl];
+                if (pl.has_clip_sample) r = fmax(r, pl.clip_sample);
+                lam += r;
+            }
+        }
+        const double n = own_row ? drow[b0 + bl] : s_data[bl];
+        double l = lam;
+        bool live = true;
+        if (pl.has_clip_bin && l < pl.clip_bin) {
+            l = pl.clip_bin;
+            live = false;
+        }
+        macc += hf_pois_term(n, l);
+        if (GRAD) {
+            // d/dl [xlogy(n, l) - l] is exactly -1 for n == 0 (also at l == 0, where n / l would be NaN)
+            const double wgt = live ? ((n == 0.0) ? -1.0 : n / l - 1.0) : 0.0;
+#pragma unroll
+            for (int s_ = 0; s_ < PM_SMAX; ++s_) {
+                if (s_ < S) {
+                    const double nom = s_nom[s_][bl];
+                    const bool lv = !(pl.has_clip_sample && F[s_] * bfs[s_] * nom < pl.clip_sample);
+                    const double wl = lv ? wgt : 0.0;
+                    G[s_] = fma(wl * bfs[s_], nom, G[s_]);  // excludes the scalar factors (finite at theta == 0)
+                    for (int k = 0; k < K; ++k) {
+                        const int p = s_bf[k][s_][bl];
+                        if (p < 0) continue;
+                        double oth = wl * F[s_] * nom;  // no division: finite for a factor sitting on 0
+                        for (int k2 = 0; k2 < K; ++k2) {
+                            const int p2 = s_bf[k2][s_][bl];
+                            if (k2 != k && p2 >= 0) oth *= w.parsT[(int64_t)p2 * ld + pt];
+                        }
+                        atomicAdd(&w.gradT[(int64_t)p * ld + pt], oth);
+                    }
+                }
+            }
+        }
+    }
+    if (GRAD && cur >= 0) {
+#pragma unroll
+        for (int s_ = 0; s_ < PM_SMAX; ++s_)
+            if (s_ < S) atomicAdd(&w.GsegT[((int64_t)s_ * NSEG + cur) * ld + pt], G[s_]);
+    }
+    atomicAdd(&w.mainv[pt], macc);
+}
+
+static int hf_main_pm_launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_point,
+                             const int* row_idx, bool grad, cudaStream_t st) {
+    const DevPlan& pl = plan->d;
+    const dim3 grid((unsigned)((ld + PM_TB - 1) / PM_TB), (unsigned)((pl.NB + PM_BT - 1) / PM_BT));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (plan->timing) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+    }
+    if (grad) hf_main_pm_kernel<true><<<grid, PM_TB, 0, st>>>(pl, plan->w, B, ld, data, per_point, row_idx);
+    else hf_main_pm_kernel<false><<<grid, PM_TB, 0, st>>>(pl, plan->w, B, ld, data, per_point, row_idx);
+    if (plan->timing) {
+        cudaEventRecord(e1, st);
+        plan->ev.push_back(e0);
+        plan->ev.push_back(e1);
+    }
+    HF_CUDA_OK(cudaGetLastError());
+    plan->launches++;
+    return HF_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // finish: constraints, scalar-factor gradients, constants, transposition to row-major
 // ------------------------------------------------------------------------------------------
@@ -909,6 +1053,16 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
     if (use_mma) {
         rc = hf_main_mma_launch(plan, B, ld, data, per_point, row_idx, do_grad, st);
         if (rc != HF_ERR_UNSUPPORTED) {
+            if (rc) return rc;
+            goto finish;
+        }
+    }
+    {
+        // histosys-free plans in batches: point-major kernel (single fits keep the bin-major one below)
+        bool use_pm = pl.H == 0 && pl.S <= PM_SMAX && pl.K <= PM_KMAX && B >= 32;
+        if (const char* e = getenv("HF_PM")) use_pm = use_pm && atoi(e) != 0;
+        if (use_pm) {
+            rc = hf_main_pm_launch(plan, B, ld, data, per_point, row_idx, do_grad, st);
             if (rc) return rc;
             goto finish;
         }
