@@ -66,6 +66,13 @@ WORKLOAD = ("C4 synthetic 1000-bin/20-channel/300-NP workspace (histosys code4p 
 NTOYS_C3 = 100000          # config 3: toys per hypothesis in total (strong scaling over the ranks)
 
 
+def bench_config(n_gpus, batch=B_PER_GPU):
+    """the `config` object of the JSON line: the SAME dict from both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch,
+            "parallelism": f"{n_gpus} independent shards (no collective)",
+            "l2": "inputs larger than L2 (pars 157 MB + grad 157 MB per step)"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,7 +264,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": WORKLOAD},
+        "data": "synthetic", "config": bench_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "fd_equivalent_value": logpdf_rate / (P + 1)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -517,10 +524,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "batch_per_gpu": B, "parallelism": f"{world} independent shards (no collective)",
-                   "l2": "inputs larger than L2 (pars 157 MB + grad 157 MB per step)",
-                   "rank0_cpu_affinity": affinity},
+        "config": bench_config(world, B), "rank0_cpu_affinity": affinity,
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

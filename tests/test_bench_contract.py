@@ -36,11 +36,12 @@ def test_reference_arm_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert cb["fd_equivalent_value"] == pytest.approx(d["value"] / 301)   # P + 1 forward differences
-    # both arms name the workload with the same string
+    # both arms print the SAME config object (one function builds it; the driver compares the two)
     import re
 
     src = open(os.path.join(ROOT, "bench.py")).read()
-    assert len(re.findall(r'"workload": WORKLOAD', src)) == 2
+    assert len(re.findall(r'"config": bench_config\(', src)) == 2
+    assert set(d["config"]) == {"workload", "batch_per_gpu", "parallelism", "l2"}
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
 
 
