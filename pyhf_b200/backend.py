@@ -33,6 +33,21 @@ class DeviceArray(torch.Tensor):
     * negative-step slices (``result_array[idx][::-1]``, infer/intervals/upper_limits.py:16-18).
     """
 
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        # the stock Tensor.__torch_function__ spends ~8 us per op in subclass checks and a generic
+        # result conversion; pyhf's p-value arithmetic is ~250 tiny ops per hypotest, more time than
+        # its five fits.  Same semantics (results come back as DeviceArray), leaner.
+        with torch._C.DisableTorchFunctionSubclass():
+            ret = func(*args, **(kwargs or {}))
+        if func in _NOWRAP:  # ._base, .grad, ...: the very object, not a fresh alias (toy tags live on it)
+            return ret
+        if type(ret) is torch.Tensor:
+            return ret.as_subclass(cls)
+        if type(ret) in (tuple, list):
+            return type(ret)(r.as_subclass(cls) if type(r) is torch.Tensor else r for r in ret)
+        return ret
+
     def __array__(self, dtype=None, copy=None):
         a = self.detach().as_subclass(torch.Tensor).cpu().numpy()
         return a if dtype is None else a.astype(dtype, copy=False)
@@ -43,6 +58,9 @@ class DeviceArray(torch.Tensor):
             index = torch.as_tensor(list(idx), dtype=torch.long, device=self.device)
             return torch.index_select(self, 0, index)
         return super().__getitem__(key)
+
+
+_NOWRAP = torch.overrides.get_default_nowrap_functions()
 
 
 def _wrap(t):
