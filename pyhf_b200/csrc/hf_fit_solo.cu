@@ -44,9 +44,12 @@ SoloLayout solo_layout(const hf_plan* plan, int ng, int nl, int Hpad, int nj, in
     const int P = pl.P, H = pl.H, S = pl.S, NSEG = pl.NSEG;
     L.xs = take(P); L.xc = take(P); L.xt = take(P); L.g = take(P); L.d = take(P);
     L.hc = take(5 * std::max(H, 1)); L.Fq = take(S * NSEG);
-    L.base = take(std::max(SMX, NT / 32) * TB); L.rS = take(SMX * TB); L.FB = take(SMX * TB);
-    L.Wt = take(TB); L.wgt = take(TB); L.w2t = take(TB); L.sqW = take(TB); L.lwj = take(TB); L.lw2 = take(TB);
-    L.gpart = take(2 * NT);  // (NT: CTA size of the instance the layout is for)
+    // bins per tile: the whole CTA for plans without histosys (no delta / derivative phases: base, FB and
+    // gpart are not used), 32 else
+    const int TBv = (H == 0) ? NT : TB;
+    L.base = take(H == 0 ? 2 : std::max(SMX, NT / 32) * TB); L.rS = take(std::min(S, SMX) * TBv); L.FB = take(H == 0 ? 2 : SMX * TB);
+    L.Wt = take(TBv); L.wgt = take(TBv); L.w2t = take(TBv); L.sqW = take(TBv); L.lwj = take(TBv); L.lw2 = take(TBv);
+    L.gpart = take(H == 0 ? 32 : 2 * NT);  // (NT: CTA size of the instance the layout is for; low 16 slots: solve scratch)
     const int npk = ng * (ng + 1) / 2;
     // the Y region doubles as DL | D2 | U0 | Msm | G2sm after the sweep and as the staging tile of C
     L.ltile = small ? 0 : 16;
@@ -55,7 +58,7 @@ SoloLayout solo_layout(const hf_plan* plan, int ng, int nl, int Hpad, int nj, in
     L.ngs = small ? (ng | 1) : ng;
     int njs = (nj + 7) / 8 * 8;
     while (njs % 16 != 8) njs += 8;
-    const int chan_small = 3 * SMX * nj + SMX * SMX + SMX + ((S * H + 1) & ~1) + (small ? 0 : plan->ah_max_lc * S);
+    const int chan_small = 2 * S * nj + ((S * nj + 1) & ~1) + SMX * SMX + SMX + ((S * H + 1) & ~1) + (small ? 0 : plan->ah_max_lc * S);
     const int chan_big = 16 * njs + ((S * nj + 1) & ~1) + SMX * SMX + SMX + 8 * Hpad + ((plan->ah_max_lc * S + 1) & ~1) + nj;
     const int chan_words = bigch ? chan_big : chan_small;
     L.ywords = std::max(std::max(H > 0 ? TB * Hpad : 0, chan_words), L.ltile * L.wstride);
@@ -65,7 +68,7 @@ SoloLayout solo_layout(const hf_plan* plan, int ng, int nl, int Hpad, int nj, in
     L.red = take(32);
     const int npj = nj * (nj + 1) / 2;
     L.lowrank = lowrank ? 1 : 0;
-    int n_int = 3 * TB + ng + nl + 8;
+    int n_int = 3 * TBv + ng + nl + 8;
     if (lowrank) {
         L.DLall = take(NSEG * S * nj); L.Qc = take(NSEG * S * S); L.vq = take(NSEG * S); L.Tq = take(NSEG * S * nj);
         L.uq = take(NSEG * S);

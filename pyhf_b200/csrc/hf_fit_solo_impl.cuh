@@ -37,6 +37,9 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
     const int P = pl.P, NB = pl.NB, S = pl.S, NSEG = pl.NSEG, H = pl.H, R = pl.R, K = pl.K;
     const int Hpad = a.Hpad, nj = a.nj, Hc = a.Hc, npart = a.npart;
     const int ng = a.ng, nl = a.nl, npk = a.npk, ngs = a.ngs;
+    // bins per tile: 32 where the histosys phases own the other warps; the whole CTA (one bin per thread)
+    // for plans without histosys -- C3's 100 bins are ONE tile, 3 barriers per sweep instead of 12
+    constexpr int TBv = (MAXT == 0) ? NT : TB;
     long long t_mark = clock64();
     auto lap = [&](int slot) {
         if (tid == 0) { const long long now = clock64(); c.prof[slot] += now - t_mark; t_mark = now; }
@@ -111,7 +114,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
     double vacc = 0.0;
     const int nsplit = (MAXT > 0) ? max(1, (NT / 32) / max(R, 1)) : 1;
 
-    for (int b0 = 0; b0 < NB; b0 += TB) {
+    for (int b0 = 0; b0 < NB; b0 += TBv) {
         // ---- (1) histosys delta of every (row, bin) of the tile
         if (MAXT > 0) {
             // every warp takes one (row, slice of the modifiers): many independent loads in flight
@@ -134,7 +137,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
             __syncthreads();
         }
         // ---- (2a) rates, value, weights, per-bin parameter
-        if (tid < TB) {
+        if (tid < TBv) {
             const int bl = tid, b = b0 + bl;
             const bool valid = b < NB;
             const int bb = valid ? b : NB - 1;
@@ -156,8 +159,8 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
                     const double fb = c.Fq[s * NSEG + seg] * bf;
                     rr[s] = valid ? fb * bs : 0.0;
                     if (FULL) {
-                        c.FB[s * TB + bl] = valid ? fb : 0.0;
-                        c.rS[s * TB + bl] = rr[s];
+                        if (MAXT > 0) c.FB[s * TBv + bl] = valid ? fb : 0.0;
+                        c.rS[s * TBv + bl] = rr[s];
                     }
                     lam += rr[s];
                 }
@@ -217,7 +220,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
         __syncthreads();
         // ---- (2b) per-segment S x S sums  M_c = sum_b W r r^T ,  G_c = sum_b wg r
         if (pair_thread || g_thread) {
-            for (int bl = 0; bl < TB && b0 + bl < NB; ++bl) {
+            for (int bl = 0; bl < TBv && b0 + bl < NB; ++bl) {
                 const int seg = c.segt[bl];
                 if (seg != mcur) {
                     if (mcur >= 0) {
@@ -227,8 +230,8 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
                     macc = 0.0;
                     mcur = seg;
                 }
-                if (pair_thread) macc = fma(c.Wt[bl] * c.rS[ps * TB + bl], c.rS[ps2 * TB + bl], macc);
-                else macc = fma(c.wgt[bl], c.rS[gs * TB + bl], macc);
+                if (pair_thread) macc = fma(c.Wt[bl] * c.rS[ps * TBv + bl], c.rS[ps2 * TBv + bl], macc);
+                else macc = fma(c.wgt[bl], c.rS[gs * TBv + bl], macc);
             }
         }
         // ---- (3) histosys columns of the tile: a_b[h], the S x H sums N_c, per-bin parameter rows
@@ -385,10 +388,10 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
     }
     __syncthreads();
     // ---------------------------------------------------------------- scalar-factor blocks, channel by channel
-    double* DL = c.Y;                  // [S][nj]  (SMX rows reserved)
-    double* D2 = DL + SMX * nj;        // [S][nj]
-    double* U0 = D2 + SMX * nj;        // [S][nj]   M_c DL
-    double* Msm = U0 + SMX * nj;       // [S][S]
+    double* DL = c.Y;                  // [S][nj]
+    double* D2 = DL + S * nj;          // [S][nj]
+    double* U0 = D2 + S * nj;          // [S][nj]   M_c DL
+    double* Msm = U0 + ((S * nj + 1) & ~1);  // [S][S]
     double* G2sm = Msm + SMX * SMX;    // [S]
     double* Ns = G2sm + SMX;           // [S][H]   N_c of the channel
     double* Lw = Ns + ((S * H + 1) & ~1);  // [locals of the channel][S]
@@ -541,7 +544,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
             // (low-rank form of the per-bin block: the channel's dlog f table is kept for the solve)
             if (lowrank) DL = c.DLall + ch * S * nj;
             for (int i = tid; i < S * nj; i += NT) DL[i] = 0.0;
-            for (int i = tid; i < SMX * nj; i += NT) D2[i] = 0.0;
+            for (int i = tid; i < S * nj; i += NT) D2[i] = 0.0;
             if (tid < S * S) Msm[tid] = c.SegM[(int64_t)ch * S * S + tid];
             if (tid < S) G2sm[tid] = c.SegG[(int64_t)ch * S + tid];
             const int li0 = pl.ah_bl_ptr[pl.ah_seg_first[ch]], li1 = pl.ah_bl_ptr[pl.ah_seg_first[ch + 1]];
@@ -1010,8 +1013,9 @@ fit_solo_kernel(DevPlan pl, SoloArgs a) {
     c.Sorig = ext + L.Sorig; c.Sred = ext + L.Sred; c.C = ext + L.C; c.SegM = ext + L.SegM; c.SegG = ext + L.SegG;
     c.SegN = ext + L.SegN; c.LOCw = ext + L.LOCw;
     int* ip = reinterpret_cast<int*>(sm + L.ints);
-    c.segt = ip; c.lgp = ip + TB; c.lmk = reinterpret_cast<unsigned*>(ip + 2 * TB);
-    c.actg = ip + 3 * TB; c.actl = c.actg + a.ng; c.flag = c.actl + a.nl;
+    constexpr int TBk = (MAXT == 0) ? NT : TB;  // bins per tile (see solo_sweep)
+    c.segt = ip; c.lgp = ip + TBk; c.lmk = reinterpret_cast<unsigned*>(ip + 2 * TBk);
+    c.actg = ip + 3 * TBk; c.actl = c.actg + a.ng; c.flag = c.actl + a.nl;
     __shared__ long long s_prof[16];
     c.prof = s_prof;
     c.DLall = sm + L.DLall; c.Qc = sm + L.Qc; c.vq = sm + L.vq; c.Tq = sm + L.Tq; c.uq = sm + L.uq;
