@@ -680,6 +680,27 @@ __device__ __forceinline__ bool chol_columns(double* S, double* linv, int n) {
     return true;
 }
 
+// systems of up to 32 unknowns: ONE warp, lane = row, values in registers, no CTA barrier inside
+// L y = r, L^T d = y for the same systems; the solution replaces r
+__device__ __forceinline__ void subst_warp(const double* S, const double* linv, double* r, int n) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
+        double ri = (lane < n) ? r[lane] : 0.0, zi = 0.0, di = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double zk = __shfl_sync(0xffffffffu, ri, k) * linv[k];
+            if (lane == k) zi = zk;
+            if (lane > k && lane < n) ri = fma(-S[tri(lane, k)], zk, ri);
+        }
+        for (int k = n - 1; k >= 0; --k) {
+            const double dk = __shfl_sync(0xffffffffu, zi, k) * linv[k];
+            if (lane == k) di = dk;
+            if (lane < k) zi = fma(-S[tri(k, lane)], dk, zi);
+        }
+        if (lane < n) r[lane] = di;
+    }
+    __syncthreads();
+}
+
 // large systems: panels of 8 columns; inside a panel one thread per row updates the <= 7 remaining
 // panel columns of its row, the trailing matrix takes the whole panel at once as 8 x 8 tiles on the
 // fp64 tensor-core path (two DMMA.8x8x4 per tile)
@@ -898,6 +919,8 @@ __device__ __forceinline__ bool solo_solve(const DevPlan& pl, const SoloArgs& a,
             __syncthreads();
         }
         lap(8);
+        // (a one-warp Cholesky, lane = row, was measured slower than the 2-barriers-per-column form on
+        //  C3's 20 x 20 system -- its trailing update is a serial chain per lane; the substitutions do gain)
         if (!bad) bad = !((ng > 48) ? chol_blocked(c.S, c.linv, ng) : chol_columns(c.S, c.linv, ng));
         lap(9);
         ok = !bad;
@@ -919,6 +942,9 @@ __device__ __forceinline__ bool solo_solve(const DevPlan& pl, const SoloArgs& a,
     attempts_out = attempts;
     if (!ok) return false;
     __syncthreads();
+    if (ng <= 32) {
+        subst_warp(c.S, c.linv, c.r, ng);
+    } else {
     // L y = r
     for (int k = 0; k < ng; ++k) {
         const double zk = c.r[k] * c.linv[k];
@@ -933,6 +959,7 @@ __device__ __forceinline__ bool solo_solve(const DevPlan& pl, const SoloArgs& a,
         for (int i = tid; i < k; i += NT) c.z[i] = fma(-c.S[tri(k, i)], dk, c.z[i]);
         if (tid == 0) c.r[k] = dk;
         __syncthreads();
+    }
     }
     lap(10);
     // d_l = -(g_l + C_l . d_g) / (H_ll + tau)
