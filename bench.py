@@ -664,7 +664,8 @@ def toy_hypotest_legs(args, batched, c4_plan, c4_data, rank, world, barrier, dis
             res5, sec5, reps5 = _timed_hypotest(torch, dist_mod, c4_plan, c4_data, n5, 7, barrier, dist, world, 1)
             legs["config5"] = {
                 "workload": "C4 (1000 bins, 300 parameters) q~ toy-based hypotest, mu = 1: BASELINE config 5 at "
-                            f"{n5} toys per hypothesis in total ({args.c4_toys_per_gpu} per GPU) instead of 10^6",
+                            f"{n5} toys per hypothesis in total ({args.c4_toys_per_gpu} per GPU)"
+                            + ("" if n5 >= 1000000 else " instead of 10^6"),
                 "ntoys_total": n5, "n_fits": 4 * n5 + 4, "n_gpus": world, "scaling": "weak", "seconds": sec5,
                 "fits_per_s": (4 * n5 + 4) / sec5, "failed_fits": res5["n_failed"],
                 "mean_newton_iterations": res5["n_iter_mean"], "CLs": res5["CLs"], "qobs": res5["qobs"],
