@@ -43,7 +43,7 @@ SoloLayout solo_layout(const hf_plan* plan, int ng, int nl, int Hpad, int nj, in
     auto take = [&](int n) { const int at = o; o += (n + 1) & ~1; return at; };
     const int P = pl.P, H = pl.H, S = pl.S, NSEG = pl.NSEG;
     L.xs = take(P); L.xc = take(P); L.xt = take(P); L.g = take(P); L.d = take(P);
-    L.hc = take(5 * std::max(H, 1)); L.Fq = take(S * NSEG);
+    L.hc = take(6 * std::max(H, 1)); L.Fq = take(S * NSEG);
     // bins per tile: the whole CTA for plans without histosys (no delta / derivative phases: base, FB and
     // gpart are not used), 32 else
     const int TBv = (H == 0) ? NT : TB;
@@ -74,6 +74,10 @@ SoloLayout solo_layout(const hf_plan* plan, int ng, int nl, int Hpad, int nj, in
         L.uq = take(NSEG * S);
         L.ppos = take((npj + 3) / 4);
         n_int += 2 * pl.ah_nbl + nj + (2 * npj + 3) / 4 + 1;
+    }
+    {
+        const int nt8max = std::max(std::max((H + 7) / 8, (ng + 7) / 8), (nj + 7) / 8) + 1;
+        L.tdec = take((nt8max * (nt8max + 1) / 2 + 3) / 4 + 1);
     }
     L.ints = take((n_int + 1) / 2 + 1);
     L.small = small ? 1 : 0;
@@ -205,6 +209,10 @@ int hf_fit_solo_launch(hf_plan* plan, const double* data, int64_t data_rows, con
     a.njs = (nj + 7) / 8 * 8;
     while (a.njs % 16 != 8) a.njs += 8;
     a.max_lc = plan->ah_max_lc;
+    {
+        const int nt8max = std::max(std::max((H + 7) / 8, (ng + 7) / 8), (nj + 7) / 8) + 1;
+        a.ntdec = nt8max * (nt8max + 1) / 2;
+    }
 
     void (*kern)(DevPlan, SoloArgs) = var->kern;
     HF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

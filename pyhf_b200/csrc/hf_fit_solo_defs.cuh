@@ -76,6 +76,7 @@ struct SoloLayout {
     int wstride;                                 // row stride of the staged rows (== 8 mod 16 doubles)
     int ngs;                                     // row stride of C
     int lowrank, DLall, Qc, vq, Tq, uq, ppos;    // low-rank form of the per-bin block: flag and offsets
+    int tdec;                                    // tile decode table
 };
 
 struct SoloArgs {
@@ -89,6 +90,7 @@ struct SoloArgs {
     int64_t trace_fit;  // HF_FIT_TRACE_FIT: index of one more fit to trace (-1: none)
     int ng, nl, npk, Hpad, nj, Hc, npart;
     int ngs;   // row stride of C
+    int ntdec;  // entries of the tile decode table
     int bigch, njs, max_lc;  // tensor-core form of the scalar-factor blocks: flag, row stride of DL / U1, locals per channel
     const int *gpos, *lpos, *glist, *llist;   // [P], [P], [ng], [nl]
     double* scratch; int64_t scratch_stride;
@@ -110,6 +112,7 @@ struct Ctx {
     int *bl2l, *blseg, *gposj;          // [n_bl] position among the per-bin parameters / channel; [nj] position among the globals
     unsigned char *pj1, *pj2;           // [nj (nj + 1) / 2] the pair of scalar-factor parameters of a packed entry
     unsigned short* ppos;               // ... and its place in the packed S_gg
+    unsigned short* tdec;               // [ntdec] (row << 8 | column) of the t-th tile of a lower triangle
     long long* prof;  // [16] clock64 sums per phase (thread 0; printed with the trace)
 };
 

@@ -3,6 +3,15 @@
 namespace SOLO_NS {
 constexpr int NT = SOLO_NT;
 
+// (a, b) of the t-th entry of a lower triangle enumerated row by row, b <= a, from the table the CTA
+// built at start-up (tri_decode costs a square root and two loops; the DMMA tile loops ask ~1500 times
+// per Newton iteration)
+__device__ __forceinline__ void tile_decode(const Ctx& c, int t, int& a, int& b) {
+    const unsigned v = c.tdec[t];
+    a = (int)(v >> 8);
+    b = (int)(v & 255u);
+}
+
 __device__ __forceinline__ double block_sum(double v, double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -72,7 +81,8 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
                 const double a2 = al * al;
                 dd = a2 * (90.0 * a2 - 120.0) + 30.0;
             }
-            c.hc[5 * h] = c1; c.hc[5 * h + 1] = c2; c.hc[5 * h + 2] = d1; c.hc[5 * h + 3] = d2; c.hc[5 * h + 4] = dd;
+            // (stride 6: the pair (c1, c2) is one 16-byte shared-memory load in the delta loop)
+            c.hc[6 * h] = c1; c.hc[6 * h + 1] = c2; c.hc[6 * h + 2] = d1; c.hc[6 * h + 3] = d2; c.hc[6 * h + 4] = dd;
         }
     }
     // product of the scalar factors of every (sample, segment): one warp per product, lanes = entries
@@ -110,7 +120,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
     for (int k = 0; k < (MAXT > 0 ? MAXT : 1); ++k) acc[k][0] = acc[k][1] = 0.0;
     const int nt8 = (H + 7) / 8, ntile = nt8 * (nt8 + 1) / 2;
     double dc1 = 0.0, dc2 = 0.0, ddc2 = 0.0;
-    if (h_thread) { dc1 = c.hc[5 * my_h + 2]; dc2 = c.hc[5 * my_h + 3]; ddc2 = c.hc[5 * my_h + 4]; }
+    if (h_thread) { dc1 = c.hc[6 * my_h + 2]; dc2 = c.hc[6 * my_h + 3]; ddc2 = c.hc[6 * my_h + 4]; }
     double vacc = 0.0;
     const int nsplit = (MAXT > 0) ? max(1, (NT / 32) / max(R, 1)) : 1;
 
@@ -129,8 +139,9 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll 8
                 for (int h = h0; h < h1; ++h) {
-                    s0 = fma(c.hc[5 * h], __ldg(p1 + h * hstride), s0);
-                    s1 = fma(c.hc[5 * h + 1], __ldg(p2 + h * hstride), s1);
+                    const double2 cc = *reinterpret_cast<const double2*>(c.hc + 6 * h);
+                    s0 = fma(cc.x, __ldg(p1 + h * hstride), s0);
+                    s1 = fma(cc.y, __ldg(p2 + h * hstride), s1);
                 }
                 c.base[warp * TB + lane] = s0 + s1;
             }
@@ -315,7 +326,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
                 const int tile = warp + (NT / 32) * k;
                 if (tile < ntile) {
                     int ti, tj;
-                    tri_decode(tile, tj, ti);  // ti <= tj : row tile, column tile
+                    tile_decode(c, tile, tj, ti);  // ti <= tj : row tile, column tile
                     const double* pa = c.Y + t4 * Hpad + 8 * ti + g8;
                     const double* pb = c.Y + t4 * Hpad + 8 * tj + g8;
 #pragma unroll
@@ -376,7 +387,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
             const int tile = warp + (NT / 32) * k;
             if (tile < ntile) {
                 int ti, tj;
-                tri_decode(tile, tj, ti);
+                tile_decode(c, tile, tj, ti);
                 const int hi = 8 * ti + g8;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -470,7 +481,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
                 const int tile = warp + (NT / 32) * q;
                 if (tile < ntsc) {
                     int ti, tj;
-                    tri_decode(tile, ti, tj);  // tj <= ti
+                    tile_decode(c, tile, ti, tj);  // tj <= ti
                     const double* pa = DLb + t4 * njs + 8 * ti + g8;
                     const double* pb = U1 + t4 * njs + 8 * tj + g8;
                     dmma884(accsc[q][0], accsc[q][1], pa[0], pb[0]);
@@ -503,7 +514,7 @@ __device__ __forceinline__ double solo_sweep(const DevPlan& pl, const SoloArgs& 
             const int tile = warp + (NT / 32) * q;
             if (tile < ntsc) {
                 int ti, tj;
-                tri_decode(tile, ti, tj);
+                tile_decode(c, tile, ti, tj);
                 const int j1 = 8 * ti + g8;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -704,7 +715,7 @@ __device__ __forceinline__ void subst_warp(const double* S, const double* linv, 
 // large systems: panels of 8 columns; inside a panel one thread per row updates the <= 7 remaining
 // panel columns of its row, the trailing matrix takes the whole panel at once as 8 x 8 tiles on the
 // fp64 tensor-core path (two DMMA.8x8x4 per tile)
-__device__ __forceinline__ bool chol_blocked(double* S, double* linv, int n) {
+__device__ __forceinline__ bool chol_blocked(const Ctx& c, double* S, double* linv, int n) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
     const int nt = (n + 7) / 8;
     for (int p = 0; p < nt; ++p) {
@@ -733,7 +744,7 @@ __device__ __forceinline__ bool chol_blocked(double* S, double* linv, int n) {
         const int ntr = nt - p - 1, ntiles = ntr * (ntr + 1) / 2;
         for (int t = warp; t < ntiles; t += NT / 32) {
             int ta, tb;
-            tri_decode(t, ta, tb);
+            tile_decode(c, t, ta, tb);
             const int ti = p + 1 + ta, tj = p + 1 + tb;
             const int i = 8 * ti + g8, k0 = 8 * tj + 2 * t4, ib = 8 * tj + g8;
             const bool ok0 = i < n && k0 <= i, ok1 = i < n && k0 + 1 <= i;
@@ -885,7 +896,7 @@ __device__ __forceinline__ bool solo_solve(const DevPlan& pl, const SoloArgs& a,
                         __syncthreads();
                         for (int t = warp; t < ntiles; t += NT / 32) {
                             int ti, tj;
-                            tri_decode(t, ti, tj);  // tj <= ti
+                            tile_decode(c, t, ti, tj);  // tj <= ti
                             const int i = 8 * ti + g8, k0 = 8 * tj + 2 * t4;
                             const bool ok0 = i < ng && k0 <= i, ok1 = i < ng && k0 + 1 <= i;
                             double d0 = ok0 ? c.S[tri(i, k0)] : 0.0, d1 = ok1 ? c.S[tri(i, k0 + 1)] : 0.0;
@@ -921,7 +932,7 @@ __device__ __forceinline__ bool solo_solve(const DevPlan& pl, const SoloArgs& a,
         lap(8);
         // (a one-warp Cholesky, lane = row, was measured slower than the 2-barriers-per-column form on
         //  C3's 20 x 20 system -- its trailing update is a serial chain per lane; the substitutions do gain)
-        if (!bad) bad = !((ng > 48) ? chol_blocked(c.S, c.linv, ng) : chol_columns(c.S, c.linv, ng));
+        if (!bad) bad = !((ng > 48) ? chol_blocked(c, c.S, c.linv, ng) : chol_columns(c.S, c.linv, ng));
         lap(9);
         ok = !bad;
         if (!ok) {
@@ -1045,6 +1056,13 @@ fit_solo_kernel(DevPlan pl, SoloArgs a) {
     c.actg = ip + 3 * TBk; c.actl = c.actg + a.ng; c.flag = c.actl + a.nl;
     __shared__ long long s_prof[16];
     c.prof = s_prof;
+    c.tdec = reinterpret_cast<unsigned short*>(sm + L.tdec);
+    for (int t = tid; t < a.ntdec; t += NT) {
+        int ta, tb;
+        tri_decode(t, ta, tb);
+        c.tdec[t] = (unsigned short)((ta << 8) | tb);
+    }
+    __syncthreads();
     c.DLall = sm + L.DLall; c.Qc = sm + L.Qc; c.vq = sm + L.vq; c.Tq = sm + L.Tq; c.uq = sm + L.uq;
     c.bl2l = c.flag + 4; c.blseg = c.bl2l + pl.ah_nbl; c.gposj = c.blseg + pl.ah_nbl;
     c.pj1 = reinterpret_cast<unsigned char*>(c.gposj + a.nj);
