@@ -162,7 +162,7 @@ constexpr int PREP_PPT = HF_PREP_PPT;      // points per thread
 constexpr int PREP_CHUNK = HF_PREP_CHUNK;  // entries of a product staged per pass (x up to 4 products)
 
 __global__ void __launch_bounds__(PREP_TB)
-hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
+hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad, int skip_hs) {
     extern __shared__ __align__(16) double prep_smem[];
     const int cap = min(max(pl.max_sf_q, 1), PREP_CHUNK);
     double* cf_s = prep_smem;                                       // [4][cap][8]
@@ -178,7 +178,9 @@ hf_prep_kernel(DevPlan pl, Work w, int64_t ld, int do_grad) {
     }
     // blockIdx.y strides over the work items: first H histosys modifiers, then the groups of
     // (sample, segment) products
-    for (int item = blockIdx.y; item < pl.H + pl.n_qg; item += gridDim.y) {
+    // (skip_hs: the DMMA kernel computes the histosys coefficients itself, their batch-major scratch --
+    //  4 x H x ld doubles, 210 MB on C4 at B = 65536 -- is neither written nor read)
+    for (int item = blockIdx.y + (skip_hs ? pl.H : 0); item < pl.H + pl.n_qg; item += gridDim.y) {
         if (item < pl.H) {
             const int h = item;
 #pragma unroll
@@ -939,12 +941,12 @@ __global__ void hf_expected_kernel(DevPlan pl, Work w, int64_t B, int64_t ld,
     out[idx] = lam;
 }
 
-static void hf_prep_launch(const DevPlan& pl, const Work& w, int64_t ld, int do_grad, cudaStream_t st) {
-    const int items = pl.H + pl.n_qg;
+static void hf_prep_launch(const DevPlan& pl, const Work& w, int64_t ld, int do_grad, cudaStream_t st, int skip_hs = 0) {
+    const int items = (skip_hs ? 0 : pl.H) + pl.n_qg;
     const int gy = items < 1 ? 1 : (items > 64 ? 64 : items);
     const dim3 grid((unsigned)((ld + PREP_TB * PREP_PPT - 1) / (PREP_TB * PREP_PPT)), (unsigned)gy);
     const size_t smem = (size_t)std::min(std::max(pl.max_sf_q, 1), PREP_CHUNK) * (4 * 64 + 8) + 16;
-    hf_prep_kernel<<<grid, PREP_TB, smem, st>>>(pl, w, ld, do_grad);
+    hf_prep_kernel<<<grid, PREP_TB, smem, st>>>(pl, w, ld, do_grad, skip_hs);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1029,8 +1031,11 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
         hf_transpose_pars_kernel<<<grid, dim3(32, 8), 0, st>>>(pl, w, pars, B, ld);
         plan->launches++;
     }
+    // tensor-core (DMMA) formulation for large batches of plans that qualify
+    bool use_mma = pl.mma_ok && B >= 256;
+    if (const char* e = getenv("HF_MMA")) use_mma = pl.mma_ok && atoi(e) != 0;
     {
-        hf_prep_launch(pl, w, ld, do_grad ? 1 : 0, st);
+        hf_prep_launch(pl, w, ld, do_grad ? 1 : 0, st, use_mma ? 1 : 0);
         plan->launches++;
     }
     // accumulators: GsegT | gradT | mainv are carved back to back (hf_ensure_work): one memset
@@ -1047,15 +1052,15 @@ int hf_eval_launch(hf_plan* plan, const double* pars, const double* data, int64_
         w.dconst = plan->dconst;
     }
 
-    // tensor-core (DMMA) formulation for large batches of plans that qualify
-    bool use_mma = pl.mma_ok && B >= 256;
-    if (const char* e = getenv("HF_MMA")) use_mma = pl.mma_ok && atoi(e) != 0;
     if (use_mma) {
         rc = hf_main_mma_launch(plan, B, ld, data, per_point, row_idx, do_grad, st);
         if (rc != HF_ERR_UNSUPPORTED) {
             if (rc) return rc;
             goto finish;
         }
+        // (did not take the batch after all: the bin-major kernel below needs the coefficient scratch)
+        hf_prep_launch(pl, w, ld, do_grad ? 1 : 0, st, 0);
+        plan->launches++;
     }
     {
         // histosys-free plans in batches: point-major kernel (single fits keep the bin-major one below)
