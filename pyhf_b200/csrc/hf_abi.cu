@@ -129,7 +129,8 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     for (int i = 0; i < d->n_gauss; ++i) { cons_kind[d->g_par[i]] = 1; cons_idx[d->g_par[i]] = i; }
     for (int i = 0; i < d->n_pois; ++i) { cons_kind[d->p_par[i]] = 2; cons_idx[d->p_par[i]] = i; }
 
-    // DMMA path tables: [tile][chunk][k_local][cell], cell = bin_local * 4 + row, zero padded
+    // DMMA path tables: [tile][half][chunk][k_local][cell], cell = (bin_local % 16) * 4 + row, zero
+    // padded: one (tile, half, chunk) block is what one half of a CTA fetches with one bulk copy
     int n_other = 0, other[2] = {-1, -1};
     for (int s = 0; s < S; ++s)
         if (sample_row[s] < 0) {
@@ -141,15 +142,15 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     const int mma_nchunks = (2 * H + HF_MMA_KC - 1) / HF_MMA_KC;
     std::vector<double> tt;
     if (mma_ok) {
-        tt.assign((size_t)mma_ntiles * mma_nchunks * HF_MMA_KC * HF_MMA_CS, 0.0);
+        tt.assign((size_t)mma_ntiles * 2 * mma_nchunks * HF_MMA_KC * HF_MMA_CSH, 0.0);
         for (int h = 0; h < H; ++h)
             for (int r = 0; r < R; ++r)
                 for (int b = 0; b < NB; ++b) {
-                    const int tile = b / HF_MMA_BT, bl = b % HF_MMA_BT, cell = bl * 4 + r;
+                    const int tile = b / HF_MMA_BT, bl = b % HF_MMA_BT, half = bl / 16, cell = (bl % 16) * 4 + r;
                     for (int which = 0; which < 2; ++which) {
                         const int k = 2 * h + which, chunk = k / HF_MMA_KC, kl = k % HF_MMA_KC;
                         const double v = (which ? d->hs_t2 : d->hs_t1)[((size_t)h * R + r) * NB + b];
-                        tt[(((size_t)tile * mma_nchunks + chunk) * HF_MMA_KC + kl) * HF_MMA_CS + cell] = v;
+                        tt[((((size_t)tile * 2 + half) * mma_nchunks + chunk) * HF_MMA_KC + kl) * HF_MMA_CSH + cell] = v;
                     }
                 }
     }

@@ -9,26 +9,35 @@
 // its operands as lane-distributed fragments: 2 doubles per lane per 256 FMAs, read from shared
 // memory conflict-free (row strides == 4 mod 16 doubles).
 //
-// One CTA (4 warps) owns HF_MMA_M = 32 parameter points and sweeps the bins in tiles of 32
+// One CTA (8 warps) owns HF_MMA_M = 32 parameter points and sweeps the bins in tiles of 32
 // (128 cells = 32 bins x 4 histosys rows):
 //   forward  Delta[pt][cell] = sum_k coef[pt][k] T[k][cell]      k = (modifier, T1|T2), K = 2H
-//            warp = 32 cells, 4x4 DMMA tiles, K streamed in chunks of 40 columns
+//            warp = 16 cells x 32 points, K streamed in chunks of 40 columns
 //   epilogue per (point, bin): factors, sample sum, Poisson term, w = n/lambda - 1, w*F -> smem
-//   backward acc[pt][k] += sum_cell wF[pt][cell] T[k][cell]       warp = 8 points, all k
+//   backward acc[pt][k] += sum_cell wF[pt][cell] T[k][cell]       warp = 8 points x 64 cells, all k
 //            accumulators stay in registers over all bin tiles, flushed once per CTA
-// Table chunks [40][132] (42 KB) are double buffered; chunk i+1 is in flight while chunk i is
-// consumed.  Reference being replaced: see hf_eval.cu.
+// The CTA is two independent HALVES of 4 warps: half h owns bins 16h .. 16h+15 of every tile
+// (cells 64h .. 64h+63) through all three phases, with its own stream of table chunks
+// [40][68] (21 KB, double buffered, bulk copies + mbarriers), its own tile constants and its own
+// named barrier.  The epilogue is a latency chain (log, reciprocal) that leaves the fp64 pipe idle;
+// the halves are free to drift apart, so that one can be in its DMMA phases while the other is in
+// its epilogue (HF_MMA_TRACE=1 prints the phase time stamps of CTA 0).  Reference being replaced:
+// see hf_eval.cu.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+
+#include <type_traits>
+#include <vector>
 
 #include "hf_internal.cuh"
 
 namespace {
 
-constexpr int BT = HF_MMA_BT, NC = HF_MMA_NC, CS = HF_MMA_CS, KC = HF_MMA_KC, MM = HF_MMA_M;
+constexpr int BT = HF_MMA_BT, CS = HF_MMA_CS, KC = HF_MMA_KC, MM = HF_MMA_M;
+constexpr int NCH_CELLS = HF_MMA_NCH, CSH = HF_MMA_CSH, HB = BT / 2;  // half tile: 64 cells, 16 bins
 constexpr int NT_BWD = KC / 8;  // n-tiles per chunk in the backward product
-constexpr uint32_t CHUNK_BYTES = KC * CS * sizeof(double);
+constexpr uint32_t CHUNK_BYTES = KC * CSH * sizeof(double);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -68,6 +77,9 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void half_barrier(int half) {  // the 128 threads of one half of the CTA
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -75,6 +87,37 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
+}
+
+// ln(x) for the Poisson term of the epilogue, where it is the longest dependency chain: table of
+// 128 intervals of the mantissa in [0.75, 1.5) (1/c_i and -ln(1/c_i) of the interval centres), then
+// ln(m) = ln(c_i) + log1p(r), r = m/c_i - 1, |r| < 2^-8, log1p as a degree-7 polynomial (next term
+// < 7e-21 absolute).  About 1 ulp; zero, denormal, negative, inf and NaN arguments go to log().
+constexpr int LOGTAB_N = 128;
+__device__ double2 g_logtab[LOGTAB_N];
+__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
+    const int hi = __double2hiint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);
+    int e = (hi >> 20) - 1023;
+    int mhi = (hi & 0x000fffff) | 0x3ff00000;
+    const int up = mhi >= 0x3ff80000;  // mantissa in [1.5, 2) -> [0.75, 1)
+    mhi -= up << 20;
+    e += up;
+    const double m = __hiloint2double(mhi, __double2loint(x));
+    const double2 t = tab[(mhi - 0x3fe80000) >> 13];
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma(r, p, 1.0 / 5.0);
+    p = fma(r, p, -1.0 / 4.0);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    const double ed = (double)e;
+    const double small = fma(ed, 1.90821492927058770002e-10, fma(r * r, p, r));
+    return fma(ed, 6.93147180369123816490e-01, t.y) + small;
+}
+__device__ __forceinline__ double pois_term_fast(double n, double lam, const double2* __restrict__ tab) {
+    const double xl = (n == 0.0 && !(lam != lam)) ? 0.0 : n * fast_log(lam, tab);
+    return xl - lam;
 }
 
 __device__ __forceinline__ double cell_factor(const DevPlan& pl, const Work& w, int64_t ld, int64_t p,
@@ -104,38 +147,53 @@ __device__ __forceinline__ void cell_bf_grad(const DevPlan& pl, const Work& w, i
 }
 
 constexpr int SMAX = 8;  // samples handled by the register-resident per-(sample, segment) sums
-constexpr int NSTAGE = 2;  // table-chunk buffers in flight (42 KB each); 3 measured no faster (also with mbarrier release)
+// table-chunk buffers per half (21 KB each).  A half (one warp per scheduler) consumes a chunk in
+// >= 1 280 cycles, a bulk copy takes ~2 500 from request to completion (HF_MMA_TRACE: with two
+// buffers the DMMA phases of a half ran at half the pipe rate, waiting for chunks), so two
+// chunks have to be in flight while the third is consumed
+constexpr int NSTAGE = 3;
 constexpr int NTHR = 256;  // 8 warps: forward = 16 cells each, backward = (8 points) x (64 cells) each
+constexpr int HTHR = NTHR / 2;  // threads of a half
 
 template <int NCH, bool GRAD, bool HASBF>
 __global__ void __launch_bounds__(NTHR, 1)
 hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
-                   int per_point, const int* __restrict__ row_idx, int KS) {
+                   int per_point, const int* __restrict__ row_idx, int KS, long long* trace, int ltab_off) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* coefs = reinterpret_cast<double*>(smem_raw);            // [MM][KS]
-    double* tbuf = coefs + (size_t)MM * KS;                          // [NSTAGE][KC*CS]
-    double* wfs2 = tbuf + NSTAGE * KC * CS;                          // [2][MM][CS]  Delta, then w*F
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wfs2 + 2 * MM * CS); // full[NSTAGE] | coefs | empty[NSTAGE]
-    int64_t* row_off = reinterpret_cast<int64_t*>(bars + 8);         // [MM]
-    // tile constants, double buffered: tile i+1 is fetched (cp.async) while tile i is worked on
-    double* nd_s2 = reinterpret_cast<double*>(row_off + MM);         // [2][MM][BT+1] observed counts
-    double* nom_s2 = nd_s2 + 2 * MM * (BT + 1);                      // [2][S][BT]    nominal of the tile
-    int* seg_s2 = reinterpret_cast<int*>(nom_s2 + 2 * SMAX * BT);    // [2][BT]
-    int* srow_s = seg_s2 + 2 * BT;                                   // [SMAX]     histosys row of a sample
-    int* bf_s2 = srow_s + SMAX;                                      // [2][K][S][BT] per-bin factor indices
-    const int bf_stride = pl.K * pl.S * BT;
+    double* tbuf_all = coefs + (size_t)MM * KS;                      // [2 halves][NSTAGE][KC*CSH]
+    double* wfs = tbuf_all + 2 * NSTAGE * KC * CSH;                  // [MM][CS]  Delta, then w*F
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(wfs + MM * CS); // per half: full[NSTAGE] | empty[NSTAGE]; [15] coefs
+    int64_t* row_off = reinterpret_cast<int64_t*>(bars_all + 16);    // [MM]
+    // tile constants: those of tile i+1 are requested (cp.async) when the epilogue of tile i is done
+    // and land during the two products that follow
+    double* nd_s = reinterpret_cast<double*>(row_off + MM);          // [MM][BT+1] observed counts
+    double* nom_s = nd_s + MM * (BT + 1);                            // [S][BT]    nominal of the tile
+    int* seg_s = reinterpret_cast<int*>(nom_s + SMAX * BT);          // [BT]
+    int* srow_s = seg_s + BT;                                        // [SMAX]     histosys row of a sample
+    int* bf_s = srow_s + SMAX;                                       // [K][S][BT] per-bin factor indices
+    double2* ltab = reinterpret_cast<double2*>(smem_raw + ltab_off); // [LOGTAB_N] table of fast_log
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int half = warp >> 2, hw = warp & 3, htid = tid & (HTHR - 1);
+    double* tbuf = tbuf_all + (size_t)half * NSTAGE * KC * CSH;
+    uint64_t* bars = bars_all + half * 2 * NSTAGE;  // full[NSTAGE] | empty[NSTAGE] of this half
+    uint64_t* bar_coefs = bars_all + 15;
     const int64_t pt0 = (int64_t)blockIdx.x * MM;
     const int NB = pl.NB, S = pl.S, ntiles = pl.mma_ntiles;
     const double* tt = pl.mma_tt;
 
     if (tid == 0) {
-        for (int i = 0; i <= NSTAGE; ++i) mbar_init(&bars[i], 1);
-        for (int i = 0; i < NSTAGE; ++i) mbar_init(&bars[NSTAGE + 1 + i], NTHR / 32);  // one arrival per warp
+        for (int hh = 0; hh < 2; ++hh) {
+            for (int i = 0; i < NSTAGE; ++i) mbar_init(&bars_all[hh * 2 * NSTAGE + i], 1);
+            for (int i = 0; i < NSTAGE; ++i)
+                mbar_init(&bars_all[hh * 2 * NSTAGE + NSTAGE + i], HTHR / 32);  // one arrival per warp of the half
+        }
+        mbar_init(bar_coefs, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (tid < LOGTAB_N) ltab[tid] = g_logtab[tid];
     if (tid < MM) {
         int64_t pt = pt0 + tid;
         if (pt >= B) pt = B - 1;
@@ -165,46 +223,50 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         noff[q] = max(pos_smp[q], 0) * BT;          // row of the tile's nominal table
         if (q >= 4 && pos_smp[q] >= 0) nother = q - 3;  // samples without histosys fill 4, 5, ...
     }
-    auto prefetch_tile = [&](int tile) {  // all threads; completion: cp_async_wait_all + barrier
-        const int b0 = tile * BT, buf = tile & 1;
-        double* nom_d = nom_s2 + buf * SMAX * BT;
-        int* bf_d = bf_s2 + buf * bf_stride;
-        for (int i = tid; i < pl.S * BT; i += NTHR) {
-            const int s = i / BT, bl = i - s * BT;
-            cp_async8(&nom_d[i], &pl.nominal[(int64_t)s * pl.NB + min(b0 + bl, pl.NB - 1)]);
+    // the threads of a half fetch the constants of the half's 16 bins; completion:
+    // cp_async_wait_all + half_barrier
+    auto prefetch_tile = [&](int tile) {
+        const int b0 = tile * BT, hb0 = HB * half;
+        for (int i = htid; i < pl.S * HB; i += HTHR) {
+            const int s = i / HB, bl = hb0 + (i - s * HB);
+            cp_async8(&nom_s[s * BT + bl], &pl.nominal[(int64_t)s * pl.NB + min(b0 + bl, pl.NB - 1)]);
         }
-        for (int i = tid; i < bf_stride; i += NTHR) {
-            const int ks = i / BT, bl = i - ks * BT;
-            cp_async4(&bf_d[i], &pl.bf_par[(int64_t)ks * pl.NB + min(b0 + bl, pl.NB - 1)]);
+        for (int i = htid; i < pl.K * pl.S * HB; i += HTHR) {
+            const int ks = i / HB, bl = hb0 + (i - ks * HB);
+            cp_async4(&bf_s[ks * BT + bl], &pl.bf_par[(int64_t)ks * pl.NB + min(b0 + bl, pl.NB - 1)]);
         }
-        if (tid < BT) cp_async4(&seg_s2[buf * BT + tid], &pl.bin_seg[min(b0 + tid, pl.NB - 1)]);
-        // observed counts of the 32 points: a warp reads one point's 32 bins per pass
-        for (int q = warp; q < MM; q += NTHR / 32)
-            cp_async8(&nd_s2[(buf * MM + q) * (BT + 1) + lane], &data[row_off[q] + min(b0 + lane, pl.NB - 1)]);
+        if (htid < HB) cp_async4(&seg_s[hb0 + htid], &pl.bin_seg[min(b0 + hb0 + htid, pl.NB - 1)]);
+        // observed counts of the 32 points: a warp reads 16 bins of two points per pass
+        for (int q = 2 * hw + (lane >> 4); q < MM; q += 2 * (HTHR / 32)) {
+            const int bl = hb0 + (lane & 15);
+            cp_async8(&nd_s[q * (BT + 1) + bl], &data[row_off[q] + min(b0 + bl, pl.NB - 1)]);
+        }
     };
     prefetch_tile(0);
-    int issued = 0;    // table chunks requested so far (thread 0)
-    int consumed = 0;  // table chunks consumed so far (uniform)
+    int issued = 0;    // table chunks of this half requested so far (uniform within the half)
+    int consumed = 0;  // table chunks of this half consumed so far (uniform within the half)
     const int per_tile = (GRAD ? 2 : 1) * NCH;
     const int n_items = ntiles * per_tile;
-    auto issue_next = [&]() {  // thread 0 only
-        if (issued < n_items) {
+    // the warps of a half take turns as the producer (lane 0 of warp `issued % 4`): a fixed producer
+    // warp falls behind the others by its waits for free buffers and the half pays the skew at its barriers
+    auto issue_next = [&]() {  // every thread of the half calls it; one lane does the work
+        if (issued < n_items && lane == 0 && hw == (issued & 3)) {
             const int tile = issued / per_tile, chunk = (issued % per_tile) % NCH;
-            // the buffer is free once every warp has arrived for the item that used it last
-            if (issued >= NSTAGE) mbar_wait(&bars[NSTAGE + 1 + issued % NSTAGE], ((issued / NSTAGE) - 1) & 1);
+            // the buffer is free once every warp of the half has arrived for the item that used it last
+            if (issued >= NSTAGE) mbar_wait(&bars[NSTAGE + issued % NSTAGE], ((issued / NSTAGE) - 1) & 1);
             uint64_t* bar = &bars[issued % NSTAGE];
             mbar_expect_tx(bar, CHUNK_BYTES);
-            bulk_g2s(tbuf + (size_t)(issued % NSTAGE) * KC * CS,
-                     tt + ((size_t)tile * NCH + chunk) * KC * CS, CHUNK_BYTES, bar);
+            bulk_g2s(tbuf + (size_t)(issued % NSTAGE) * KC * CSH,
+                     tt + (((size_t)tile * 2 + half) * NCH + chunk) * KC * CSH, CHUNK_BYTES, bar);
         }
         ++issued;
     };
     if (tid == 0) {
-        mbar_expect_tx(&bars[NSTAGE], (uint32_t)(MM * KS * sizeof(double)));
-        bulk_g2s(coefs, w.coefK + pt0 * KS, (uint32_t)(MM * KS * sizeof(double)), &bars[NSTAGE]);
-        for (int i = 0; i < NSTAGE - 1; ++i) issue_next();  // prologue: NSTAGE-1 chunks in flight
+        mbar_expect_tx(bar_coefs, (uint32_t)(MM * KS * sizeof(double)));
+        bulk_g2s(coefs, w.coefK + pt0 * KS, (uint32_t)(MM * KS * sizeof(double)), bar_coefs);
     }
-    mbar_wait(&bars[NSTAGE], 0);
+    for (int i = 0; i < NSTAGE - 1; ++i) issue_next();  // prologue: NSTAGE-1 chunks in flight
+    mbar_wait(bar_coefs, 0);
 
     // backward accumulators: this warp's 8 points x all K columns
     double bacc[NCH][NT_BWD][2];
@@ -225,11 +287,9 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     const int ra = 2 * (t & 1);
 
     for (int tile = 0; tile < ntiles; ++tile) {
-        // Delta / w*F of consecutive tiles alternate between two buffers: a warp that is ahead
-        // writes the next tile's Delta while a slow one still reads this tile's w*F in the
-        // backward product (the buffer it writes was last read two tiles ago, and two CTA
-        // barriers lie in between)
-        double* wfs = wfs2 + (size_t)(tile & 1) * MM * CS;
+        // HF_MMA_TRACE: phase time stamps of the first CTA, [half][tile][forward, epilogue, backward, end]
+        const bool tr = trace != nullptr && blockIdx.x == 0 && hw == 0 && lane == 0;
+        if (tr) trace[(half * ntiles + tile) * 4 + 0] = clock64();
         // ---------------------------------------------------------------- forward contraction
         {
             double facc[4][2][2];
@@ -239,17 +299,17 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 for (int ni = 0; ni < 2; ++ni) facc[mi][ni][0] = facc[mi][ni][1] = 0.0;
 #pragma unroll 1
             for (int chunk = 0; chunk < NCH; ++chunk) {
-                if (tid == 0) issue_next();
+                issue_next();
                 mbar_wait(&bars[consumed % NSTAGE], (consumed / NSTAGE) & 1);
-                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CS + 16 * warp + g;
+                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + 16 * hw + g;
                 const double* ca = coefs + (size_t)g * KS + chunk * KC + t;
-#pragma unroll 5
+#pragma unroll
                 for (int k4 = 0; k4 < KC / 4; ++k4) {
                     double a[4], b[2];
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) a[mi] = ca[(size_t)(8 * mi) * KS + k4 * 4];
 #pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) b[ni] = tb[(k4 * 4 + t) * CS + 8 * ni];
+                    for (int ni = 0; ni < 2; ++ni) b[ni] = tb[(k4 * 4 + t) * CSH + 8 * ni];
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -258,11 +318,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 }
                 // this warp is done with the buffer (no CTA-wide barrier: warps may run one chunk apart)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[NSTAGE + 1 + consumed % NSTAGE]);
+                if (lane == 0) mbar_arrive(&bars[NSTAGE + consumed % NSTAGE]);
                 ++consumed;
             }
             // Delta fragments -> shared [point][cell]; lane owns point 8mi+g, bin 4*warp+2ni+(t>>1),
-            // rows ra, ra+1 of every (mi, ni) tile
+            // rows ra, ra+1 of every (mi, ni) tile.  The cells still hold w*F of the previous tile
+            // until every warp of the half has left its backward product.
+            half_barrier(half);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -274,16 +336,11 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     *reinterpret_cast<double2*>(&wfs[(size_t)(8 * mi + g) * CS + 4 * bl + ra]) = st;
                 }
         }
-        // ---- the tile's model constants were requested one tile ago (prefetch_tile): make them
-        //      visible, then request the next tile's into the other buffer (its last readers, the
-        //      epilogue of tile - 1, are past the barrier above)
+        // ---- the tile's model constants were requested after the previous epilogue: make them and
+        //      the Delta tile visible
         cp_async_wait_all();
-        __syncthreads();
-        if (tile + 1 < ntiles) prefetch_tile(tile + 1);
-        const double* nd_s = nd_s2 + (tile & 1) * MM * (BT + 1);
-        const double* nom_s = nom_s2 + (tile & 1) * SMAX * BT;
-        const int* seg_s = seg_s2 + (tile & 1) * BT;
-        const int* bf_s = bf_s2 + (tile & 1) * bf_stride;
+        half_barrier(half);
+        if (tr) trace[(half * ntiles + tile) * 4 + 1] = clock64();
 
         // ---------------------------------------------------------------- epilogue
         // positions 0..3 are the histosys rows (Delta in cell[0..3]), 4..7 the other samples.
@@ -306,18 +363,47 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             gseg = seg;
         };
         const int seg_first = seg_s[4 * warp], seg_last = seg_s[4 * warp + 3];
-        bool plain = true;  // none of the warp's 4 bins carries a per-bin factor
+        // per-bin factors of the warp's 4 bins: none, or (K == 1: staterror / shapesys / shapefactor alone)
+        // ONE parameter per bin, shared by the samples that carry it (gmask: bit = sample position);
+        // anything else takes the general path below
+        bool simple = true;
+        int gpar[4] = {-1, -1, -1, -1};
+        unsigned gmask[4] = {0u, 0u, 0u, 0u};
         if (HASBF) {
-            for (int ks = 0; ks < pl.K * S; ++ks) {
-                const int* r4 = bf_s + ks * BT + 4 * warp;
-                plain = plain && ((r4[0] & r4[1] & r4[2] & r4[3]) < 0);
+            if (pl.K == 1) {
+#pragma unroll
+                for (int q = 0; q < SMAX; ++q) {
+                    if (pos_smp[q] < 0) continue;
+                    const int* r4 = bf_s + pos_smp[q] * BT + 4 * warp;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int par = r4[j];
+                        if (par < 0) continue;
+                        if (gpar[j] >= 0 && gpar[j] != par) simple = false;
+                        gpar[j] = par;
+                        gmask[j] |= 1u << q;
+                    }
+                }
+            } else {
+                for (int ks = 0; ks < pl.K * S; ++ks) {
+                    const int* r4 = bf_s + ks * BT + 4 * warp;
+                    simple = simple && ((r4[0] & r4[1] & r4[2] & r4[3]) < 0);
+                }
             }
         }
+        const bool hasg = HASBF && (gpar[0] >= 0 || gpar[1] >= 0 || gpar[2] >= 0 || gpar[3] >= 0);
         // bins are ordered, so the warp's 4 bins span at most two segments iff the inner ones
         // belong to the first or the last one; each segment gets one (masked) pass
         const bool two_seg = (seg_s[4 * warp + 1] == seg_first || seg_s[4 * warp + 1] == seg_last) &&
                              (seg_s[4 * warp + 2] == seg_first || seg_s[4 * warp + 2] == seg_last);
-        if (plain && two_seg) {
+        // the 4 bins as 4 interleaved dependency chains; WG: some of them carry a per-bin parameter
+        auto fast_bins = [&](auto wg_tag) {
+            constexpr bool WG = decltype(wg_tag)::value;
+            double gam[4];
+            if (WG) {  // the four loads are in flight together
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gam[j] = (gpar[j] >= 0) ? w.parsT[(int64_t)gpar[j] * ld + p] : 1.0;
+            }
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int seg_cur = pass ? seg_last : seg_first;
@@ -339,7 +425,9 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                         if (q < 5 || q < 4 + nother) {
                             double base = nom_s[noff[q] + bl];
                             if (q < 4) base += dl[q];
-                            acc = fma(fseg[q], base, acc);
+                            double f = fseg[q];
+                            if (WG) f *= ((gmask[j] >> q) & 1u) ? gam[j] : 1.0;
+                            acc = fma(f, base, acc);
                         }
                     }
                     lam[j] = acc;
@@ -349,7 +437,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     const int bl = 4 * warp + j;
                     const bool valid = (tile * BT + bl < NB) && act[j];
                     const double n = nd_s[lane * (BT + 1) + bl];
-                    if (valid) val += hf_pois_term(n, lam[j]);
+                    if (valid) val += pois_term_fast(n, lam[j], ltab);
                     // n * rcp(lambda) (correctly rounded reciprocal + one FMA) instead of the IEEE divide:
                     // <= 1.5 ulp on n/lambda, same inf / NaN behaviour at lambda = 0
                     // (n == 0: the derivative of xlogy(0, l) - l is exactly -1, also at l == 0)
@@ -364,21 +452,34 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                         const double4 dlt = *reinterpret_cast<const double4*>(cell);
                         const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
                         double wf[4];
+                        double gsum = 0.0;  // d lambda / d gamma of the bin's parameter
 #pragma unroll
                         for (int q = 0; q < SMAX; ++q) {
                             if (q < 5 || q < 4 + nother) {
                                 double base = nom_s[noff[q] + bl];
                                 if (q < 4) base += dl[q];
-                                gacc[q] = fma(wgt[j], base, gacc[q]);  // (never flushed for empty positions)
-                                if (q < 4) wf[q] = wgt[j] * fseg[q];
+                                double wq = wgt[j];
+                                if (WG) {
+                                    const bool on = (gmask[j] >> q) & 1u;
+                                    wq *= on ? gam[j] : 1.0;
+                                    gsum = fma(on ? fseg[q] : 0.0, base, gsum);
+                                }
+                                gacc[q] = fma(wq, base, gacc[q]);  // (never flushed for empty positions)
+                                if (q < 4) wf[q] = wq * fseg[q];
                             }
                         }
                         double4 st;  // A' operand of the backward product
                         st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
                         *reinterpret_cast<double4*>(cell) = st;
+                        if (WG && gpar[j] >= 0 && wgt[j] != 0.0)
+                            atomicAdd(&w.gradT[(int64_t)gpar[j] * ld + p], wgt[j] * gsum);
                     }
                 }
             }
+        };
+        if (simple && two_seg) {
+            if (hasg) fast_bins(std::true_type{});
+            else fast_bins(std::false_type{});
         } else {
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
@@ -435,30 +536,32 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         }
 
         // ---------------------------------------------------------------- backward contraction
+        half_barrier(half);  // w*F of the half's 16 bins complete, tile constants free
+        if (tr) trace[(half * ntiles + tile) * 4 + 2] = clock64();
+        if (tile + 1 < ntiles) prefetch_tile(tile + 1);
         if (GRAD) {
-            __syncthreads();  // w*F tile complete
 #pragma unroll
             for (int chunk = 0; chunk < NCH; ++chunk) {
-                if (tid == 0) issue_next();
+                issue_next();
                 mbar_wait(&bars[consumed % NSTAGE], (consumed / NSTAGE) & 1);
-                // warp = (m-tile: points 8*(warp&3)+g) x (cell half: 64*(warp>>2) ..)
-                const int c0 = 64 * (warp >> 2);
-                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CS + (size_t)g * CS + t + c0;
-                const double* arow = wfs + (size_t)(8 * (warp & 3) + g) * CS + t + c0;
-#pragma unroll 4
-                for (int c4 = 0; c4 < NC / 8; ++c4) {
+                // warp = (m-tile: points 8*hw+g) x (the half's 64 cells)
+                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + (size_t)g * CSH + t;
+                const double* arow = wfs + (size_t)(8 * hw + g) * CS + t + NCH_CELLS * half;
+#pragma unroll
+                for (int c4 = 0; c4 < NCH_CELLS / 4; ++c4) {
                     const double a = arow[4 * c4];
 #pragma unroll
                     for (int ni = 0; ni < NT_BWD; ++ni) {
-                        const double b = tb[(size_t)(8 * ni) * CS + 4 * c4];
+                        const double b = tb[(size_t)(8 * ni) * CSH + 4 * c4];
                         dmma884(bacc[chunk][ni][0], bacc[chunk][ni][1], a, b);
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[NSTAGE + 1 + consumed % NSTAGE]);
+                if (lane == 0) mbar_arrive(&bars[NSTAGE + consumed % NSTAGE]);
                 ++consumed;
             }
         }
+        if (tr) trace[(half * ntiles + tile) * 4 + 3] = clock64();
     }
 
     // ---------------------------------------------------------------- flush
@@ -505,18 +608,46 @@ __global__ void hf_prep_mma_kernel(DevPlan pl, Work w, int64_t ld, int KS) {
     *reinterpret_cast<double2*>(&w.coefK[pt * KS + 2 * h]) = v;
 }
 
+// table of fast_log: (1/c_i rounded, -ln of that rounded value) -- uploaded once per device
+int upload_logtab() {
+    static bool done[64] = {};
+    int dev = 0;
+    HF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done[dev]) return HF_OK;
+    double2 h[LOGTAB_N];
+    for (int i = 0; i < LOGTAB_N; ++i) {
+        const long double c = i < 64 ? 0.75L + (i + 0.5L) / 256.0L : 1.0L + (i - 64 + 0.5L) / 128.0L;
+        h[i].x = (double)(1.0L / c);
+        h[i].y = (double)(-logl((long double)h[i].x));
+    }
+    HF_CUDA_OK(cudaMemcpyToSymbol(g_logtab, h, sizeof(h)));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return HF_OK;
+}
+
 template <int NCH>
 int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_point,
            const int* row_idx, bool grad, cudaStream_t st) {
     const DevPlan& pl = plan->d;
     const int KS = hf_mma_ks(pl.H);
-    size_t smem = sizeof(double) * ((size_t)MM * KS + NSTAGE * KC * CS + 2 * MM * CS) + 64 + 8 * MM + 128 +
-                  2 * sizeof(double) * (MM * (BT + 1) + SMAX * BT) +
-                  sizeof(int) * (2 * BT + SMAX + 2 * (size_t)pl.K * pl.S * BT) + 64;
+    size_t smem = sizeof(double) * ((size_t)MM * KS + 2 * NSTAGE * KC * CSH + MM * CS) + 128 + 8 * MM + 128 +
+                  sizeof(double) * (MM * (BT + 1) + SMAX * BT) +
+                  sizeof(int) * (BT + SMAX + (size_t)pl.K * pl.S * BT) + 64;
+    smem = (smem + 15) / 16 * 16;
+    const int ltab_off = (int)smem;
+    smem += sizeof(double2) * LOGTAB_N;
+    if (smem > 227 * 1024) return HF_ERR_UNSUPPORTED;  // (many histosys / per-bin factor kinds: bin-major kernel)
     const int64_t half = KS / 2;
     hf_prep_mma_kernel<<<(unsigned)((ld * half + 255) / 256), 256, 0, st>>>(pl, plan->w, ld, KS);
     plan->launches++;
     const dim3 grid((unsigned)(ld / MM));
+    if (const int rc_tab = upload_logtab()) return rc_tab;
+    long long* trace = nullptr;
+    static const bool want_trace = getenv("HF_MMA_TRACE") && atoi(getenv("HF_MMA_TRACE")) != 0;
+    if (want_trace) {
+        HF_CUDA_OK(cudaMalloc(&trace, sizeof(long long) * 8 * pl.mma_ntiles));
+        HF_CUDA_OK(cudaMemsetAsync(trace, 0, sizeof(long long) * 8 * pl.mma_ntiles, st));
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (plan->timing) {
         cudaEventCreate(&e0);
@@ -527,7 +658,7 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
     {                                                                                               \
         auto k = hf_main_mma_kernel<NCH, G_, BF_>;                                                  \
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k<<<grid, NTHR, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS);              \
+        k<<<grid, NTHR, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS, trace, ltab_off); \
     }
     if (grad) {
         if (pl.K > 0) HF_MMA_GO(true, true) else HF_MMA_GO(true, false)
@@ -542,6 +673,23 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
     }
     HF_CUDA_OK(cudaGetLastError());
     plan->launches++;
+    if (trace) {  // diagnostic: cycles of the phases of CTA 0, relative to the first stamp
+        std::vector<long long> h(8 * (size_t)pl.mma_ntiles);
+        HF_CUDA_OK(cudaStreamSynchronize(st));
+        HF_CUDA_OK(cudaMemcpy(h.data(), trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        long long t0 = h[0];
+        for (long long v : h) if (v && v < t0) t0 = v;
+        for (int tile = 0; tile < pl.mma_ntiles; ++tile) {
+            fprintf(stderr, "mma-trace tile %2d", tile);
+            for (int hh = 0; hh < 2; ++hh) {
+                const long long* r = &h[((size_t)hh * pl.mma_ntiles + tile) * 4];
+                fprintf(stderr, " | half %d F@%7lld E@%7lld B@%7lld end@%7lld (F %5lld E %5lld B %5lld)", hh, r[0] - t0,
+                        r[1] - t0, r[2] - t0, r[3] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2]);
+            }
+            fprintf(stderr, "\n");
+        }
+    }
     return HF_OK;
 }
 

@@ -51,7 +51,7 @@ struct DevPlan {
     int mma_nchunks;             // K chunks of HF_MMA_KC columns (column 2h = T1_h, 2h+1 = T2_h)
     int mma_nother;              // samples without histosys
     int mma_other[2];            // their sample indices
-    const double* mma_tt;        // [ntiles][nchunks][HF_MMA_KC][HF_MMA_CS] (cell = bin_local*4 + row)
+    const double* mma_tt;        // [ntiles][2 halves][nchunks][HF_MMA_KC][HF_MMA_CSH] (cell = (bin_local % 16)*4 + row)
     // ---- analytic Hessian (hf_hess_analytic.cu)
     int ah_ok;                   // plan qualifies (else the minimiser differences the analytic gradient)
     int ah_nsfp;                 // distinct parameters among the scalar-factor entries
@@ -71,6 +71,8 @@ struct DevPlan {
 #define HF_MMA_BT 32    // bins per tile
 #define HF_MMA_NC 128   // cells per tile (4 rows per bin)
 #define HF_MMA_CS 132   // padded cell stride: == 4 mod 16 doubles -> conflict-free fragment loads
+#define HF_MMA_NCH 64   // cells of a half tile (16 bins): the unit one half of the CTA (4 warps) works on
+#define HF_MMA_CSH 68   // padded cell stride of a half-tile table chunk (== 4 mod 16 doubles)
 #define HF_MMA_KC 40    // K columns per chunk (20 modifiers)
 #define HF_MMA_M 32     // parameter points per CTA
 
