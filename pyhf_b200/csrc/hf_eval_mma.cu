@@ -155,7 +155,9 @@ constexpr int NSTAGE = 3;
 constexpr int NTHR = 256;  // 8 warps: forward = 16 cells each, backward = (8 points) x (64 cells) each
 constexpr int HTHR = NTHR / 2;  // threads of a half
 
-template <int NCH, bool GRAD, bool HASBF>
+// NPOS: sample positions kept in registers (0..3 the histosys rows, 4.. the samples without histosys);
+// 5 covers plans with at most one histosys-free sample and keeps 18 registers free for the products
+template <int NCH, bool GRAD, bool HASBF, int NPOS>
 __global__ void __launch_bounds__(NTHR, 1)
 hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
                    int per_point, const int* __restrict__ row_idx, int KS, long long* trace, int ltab_off) {
@@ -216,9 +218,9 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         srow_s[tid] = smp;
     }
     __syncthreads();
-    int pos_smp[SMAX], noff[SMAX], nother = 0;
+    int pos_smp[NPOS], noff[NPOS], nother = 0;
 #pragma unroll
-    for (int q = 0; q < SMAX; ++q) {
+    for (int q = 0; q < NPOS; ++q) {
         pos_smp[q] = srow_s[q];
         noff[q] = max(pos_smp[q], 0) * BT;          // row of the tile's nominal table
         if (q >= 4 && pos_smp[q] >= 0) nother = q - 3;  // samples without histosys fill 4, 5, ...
@@ -279,11 +281,11 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     // epilogue state: thread = point `lane`, warp = 8 consecutive bins of every tile
     const int64_t p = pt0 + lane;
     double val = 0.0;      // main-term partial sum of this point over this warp's bins
-    double gacc[SMAX];     // per-sample sums of w*bf*base inside the current segment
-    double fseg[SMAX];     // scalar-factor products of this point in the current segment
+    double gacc[NPOS];     // per-sample sums of w*bf*base inside the current segment
+    double fseg[NPOS];     // scalar-factor products of this point in the current segment
     int gseg = -1;
 #pragma unroll
-    for (int s = 0; s < SMAX; ++s) gacc[s] = fseg[s] = 0.0;
+    for (int s = 0; s < NPOS; ++s) gacc[s] = fseg[s] = 0.0;
     const int ra = 2 * (t & 1);
 
     for (int tile = 0; tile < ntiles; ++tile) {
@@ -350,12 +352,12 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         auto switch_segment = [&](int seg) {
             if (GRAD && gseg >= 0) {
 #pragma unroll
-                for (int q = 0; q < SMAX; ++q)
+                for (int q = 0; q < NPOS; ++q)
                     if (pos_smp[q] >= 0 && gacc[q] != 0.0)
                         atomicAdd(&w.GsegT[((int64_t)pos_smp[q] * pl.NSEG + gseg) * ld + p], gacc[q]);
             }
 #pragma unroll
-            for (int q = 0; q < SMAX; ++q) {
+            for (int q = 0; q < NPOS; ++q) {
                 gacc[q] = 0.0;
                 // scalar factors of this point in the new segment stay in registers
                 fseg[q] = (pos_smp[q] >= 0) ? w.FsegT[((int64_t)pos_smp[q] * pl.NSEG + seg) * ld + p] : 0.0;
@@ -372,7 +374,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         if (HASBF) {
             if (pl.K == 1) {
 #pragma unroll
-                for (int q = 0; q < SMAX; ++q) {
+                for (int q = 0; q < NPOS; ++q) {
                     if (pos_smp[q] < 0) continue;
                     const int* r4 = bf_s + pos_smp[q] * BT + 4 * warp;
 #pragma unroll
@@ -421,7 +423,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     // (only the rarely used positions 5..7 keep a uniform guard)
                     double acc = 0.0;
 #pragma unroll
-                    for (int q = 0; q < SMAX; ++q) {
+                    for (int q = 0; q < NPOS; ++q) {
                         if (q < 5 || q < 4 + nother) {
                             double base = nom_s[noff[q] + bl];
                             if (q < 4) base += dl[q];
@@ -454,7 +456,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                         double wf[4];
                         double gsum = 0.0;  // d lambda / d gamma of the bin's parameter
 #pragma unroll
-                        for (int q = 0; q < SMAX; ++q) {
+                        for (int q = 0; q < NPOS; ++q) {
                             if (q < 5 || q < 4 + nother) {
                                 double base = nom_s[noff[q] + bl];
                                 if (q < 4) base += dl[q];
@@ -491,13 +493,13 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             double* cell = wfs + (size_t)lane * CS + 4 * bl;
             if (seg != gseg) switch_segment(seg);  // warp-uniform: all lanes look at the same bin
             const double4 dlt = *reinterpret_cast<const double4*>(cell);
-            double basev[SMAX], bfv[SMAX];
+            double basev[NPOS], bfv[NPOS];
             basev[0] = dlt.x; basev[1] = dlt.y; basev[2] = dlt.z; basev[3] = dlt.w;
 #pragma unroll
-            for (int q = 4; q < SMAX; ++q) basev[q] = 0.0;
+            for (int q = 4; q < NPOS; ++q) basev[q] = 0.0;
             double lam = 0.0;
 #pragma unroll
-            for (int q = 0; q < SMAX; ++q) {
+            for (int q = 0; q < NPOS; ++q) {
                 bfv[q] = 1.0;
                 if (pos_smp[q] >= 0) {
                     const int s = pos_smp[q];
@@ -517,7 +519,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 const double wgt = valid ? ((n == 0.0) ? -1.0 : n / lam - 1.0) : 0.0;
                 double wf[4];
 #pragma unroll
-                for (int q = 0; q < SMAX; ++q) {
+                for (int q = 0; q < NPOS; ++q) {
                     if (pos_smp[q] >= 0) {
                         const double wb = wgt * bfv[q];
                         gacc[q] = fma(wb, basev[q], gacc[q]);
@@ -569,7 +571,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     if (GRAD) {
         if (gseg >= 0) {
 #pragma unroll
-            for (int q = 0; q < SMAX; ++q)
+            for (int q = 0; q < NPOS; ++q)
                 if (pos_smp[q] >= 0 && gacc[q] != 0.0)
                     atomicAdd(&w.GsegT[((int64_t)pos_smp[q] * pl.NSEG + gseg) * ld + p], gacc[q]);
         }
@@ -654,18 +656,21 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
         cudaEventCreate(&e1);
         cudaEventRecord(e0, st);
     }
-#define HF_MMA_GO(G_, BF_)                                                                          \
+#define HF_MMA_GO2(G_, BF_, NP_)                                                                       \
     {                                                                                               \
-        auto k = hf_main_mma_kernel<NCH, G_, BF_>;                                                  \
+        auto k = hf_main_mma_kernel<NCH, G_, BF_, NP_>;                                               \
         HF_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k<<<grid, NTHR, smem, st>>>(pl, plan->w, B, ld, data, per_point, row_idx, KS, trace, ltab_off); \
     }
+#define HF_MMA_GO(G_, BF_) \
+    { if (pl.S - pl.R <= 1) HF_MMA_GO2(G_, BF_, 5) else HF_MMA_GO2(G_, BF_, SMAX) }
     if (grad) {
         if (pl.K > 0) HF_MMA_GO(true, true) else HF_MMA_GO(true, false)
     } else {
         if (pl.K > 0) HF_MMA_GO(false, true) else HF_MMA_GO(false, false)
     }
 #undef HF_MMA_GO
+#undef HF_MMA_GO2
     if (plan->timing) {
         cudaEventRecord(e1, st);
         plan->ev.push_back(e0);
