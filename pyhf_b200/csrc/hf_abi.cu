@@ -368,8 +368,8 @@ int hf_ensure_work(hf_plan* plan, int64_t ld, int64_t data_rows) {
         plan->work_block = nullptr;
         plan->work_ld = 0;
         const int64_t nq = (int64_t)pl.S * pl.NSEG;
-        // [parsT P][c1,c2,dc1,dc2 4H][Fseg,Gseg 2nq][gradT P][mainv 1][coefK KS]
-        const int64_t rows = 2LL * pl.P + 4LL * pl.H + 2 * nq + 1 + (pl.mma_ok ? hf_mma_ks(pl.H) : 0) + 8;
+        // [parsT P][c1,c2,dc1,dc2 4H][Fseg,Gseg 2nq][gradT P][mainv 1]
+        const int64_t rows = 2LL * pl.P + 4LL * pl.H + 2 * nq + 1 + 8;
         const size_t bytes = sizeof(double) * (size_t)rows * (size_t)ld + 256;
         cudaError_t e = cudaMalloc(&plan->work_block, bytes);
         if (e != cudaSuccess) {
@@ -392,8 +392,6 @@ int hf_ensure_work(hf_plan* plan, int64_t ld, int64_t data_rows) {
         w.GsegT = p; p += nq * ld;               // GsegT | gradT | mainv stay adjacent: hf_eval_launch
         w.gradT = p; p += (int64_t)pl.P * ld;     // clears the three accumulators with one memset
         w.mainv = p; p += ld;
-        p = (double*)(((uintptr_t)p + 255) / 256 * 256);
-        w.coefK = p;
     }
     if (data_rows > plan->dconst_cap) {
         if (plan->dconst) cudaFree(plan->dconst);

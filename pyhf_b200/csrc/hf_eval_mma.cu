@@ -165,7 +165,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     double* coefs = reinterpret_cast<double*>(smem_raw);            // [MM][KS]
     double* tbuf_all = coefs + (size_t)MM * KS;                      // [2 halves][NSTAGE][KC*CSH]
     double* wfs = tbuf_all + 2 * NSTAGE * KC * CSH;                  // [MM][CS]  Delta, then w*F
-    uint64_t* bars_all = reinterpret_cast<uint64_t*>(wfs + MM * CS); // per half: full[NSTAGE] | empty[NSTAGE]; [15] coefs
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(wfs + MM * CS); // per half: full[NSTAGE] | empty[NSTAGE]
     int64_t* row_off = reinterpret_cast<int64_t*>(bars_all + 16);    // [MM]
     // tile constants: those of tile i+1 are requested (cp.async) when the epilogue of tile i is done
     // and land during the two products that follow
@@ -180,7 +180,6 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     const int half = warp >> 2, hw = warp & 3, htid = tid & (HTHR - 1);
     double* tbuf = tbuf_all + (size_t)half * NSTAGE * KC * CSH;
     uint64_t* bars = bars_all + half * 2 * NSTAGE;  // full[NSTAGE] | empty[NSTAGE] of this half
-    uint64_t* bar_coefs = bars_all + 15;
     const int64_t pt0 = (int64_t)blockIdx.x * MM;
     const int NB = pl.NB, S = pl.S, ntiles = pl.mma_ntiles;
     const double* tt = pl.mma_tt;
@@ -191,7 +190,6 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             for (int i = 0; i < NSTAGE; ++i)
                 mbar_init(&bars_all[hh * 2 * NSTAGE + NSTAGE + i], HTHR / 32);  // one arrival per warp of the half
         }
-        mbar_init(bar_coefs, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -263,12 +261,21 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         }
         ++issued;
     };
-    if (tid == 0) {
-        mbar_expect_tx(bar_coefs, (uint32_t)(MM * KS * sizeof(double)));
-        bulk_g2s(coefs, w.coefK + pt0 * KS, (uint32_t)(MM * KS * sizeof(double)), bar_coefs);
-    }
     for (int i = 0; i < NSTAGE - 1; ++i) issue_next();  // prologue: NSTAGE-1 chunks in flight
-    mbar_wait(bar_coefs, 0);
+    // A operand of the forward product: the histosys coefficients (c1_h, c2_h) of the CTA's 32 points,
+    // point-major rows of KS doubles (zero padded), computed here from the batch-major parameters
+    // (lanes = consecutive points: coalesced reads) instead of travelling through a global scratch
+    for (int i = tid; i < (KS / 2) * MM; i += NTHR) {
+        const int h = i / MM, pt = i - h * MM;
+        double2 v;
+        v.x = v.y = 0.0;
+        if (h < pl.H) {
+            double d1, d2;
+            hf_hs_coeffs(pl.hs_code, w.parsT[(int64_t)pl.hs_par[h] * ld + pt0 + pt], v.x, v.y, d1, d2);
+        }
+        *reinterpret_cast<double2*>(&coefs[(size_t)pt * KS + 2 * h]) = v;
+    }
+    __syncthreads();
 
     // backward accumulators: this warp's 8 points x all K columns
     double bacc[NCH][NT_BWD][2];
@@ -584,30 +591,16 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 const int h = (chunk * KC + 8 * ni + 2 * t) >> 1;
                 if (h < pl.H) {
                     const int par = pl.hs_par[h];
+                    // alpha of (point, modifier) from the coefficient block: c1 (code4p), c1 + c2 (code0)
+                    const double2 cc = *reinterpret_cast<const double2*>(&coefs[(size_t)(8 * hw + g) * KS + 2 * h]);
+                    const double alpha = (pl.hs_code == HF_HS_CODE4P) ? cc.x : cc.x + cc.y;
                     double c1, c2, d1, d2;
-                    hf_hs_coeffs(pl.hs_code, w.parsT[(int64_t)par * ld + pw], c1, c2, d1, d2);
+                    hf_hs_coeffs(pl.hs_code, alpha, c1, c2, d1, d2);
                     atomicAdd(&w.gradT[(int64_t)par * ld + pw],
                               d1 * bacc[chunk][ni][0] + d2 * bacc[chunk][ni][1]);
                 }
             }
     }
-}
-
-// point-major coefficient rows for the A operand: coefK[pt][2h] = c1_h, [2h+1] = c2_h, zero padded
-__global__ void hf_prep_mma_kernel(DevPlan pl, Work w, int64_t ld, int KS) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int half = KS / 2;
-    if (idx >= ld * half) return;
-    const int64_t pt = idx / half;
-    const int h = (int)(idx - pt * half);
-    double2 v;
-    v.x = 0.0;
-    v.y = 0.0;
-    if (h < pl.H) {
-        double d1, d2;
-        hf_hs_coeffs(pl.hs_code, w.parsT[(int64_t)pl.hs_par[h] * ld + pt], v.x, v.y, d1, d2);
-    }
-    *reinterpret_cast<double2*>(&w.coefK[pt * KS + 2 * h]) = v;
 }
 
 // table of fast_log: (1/c_i rounded, -ln of that rounded value) -- uploaded once per device
@@ -639,9 +632,6 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
     const int ltab_off = (int)smem;
     smem += sizeof(double2) * LOGTAB_N;
     if (smem > 227 * 1024) return HF_ERR_UNSUPPORTED;  // (many histosys / per-bin factor kinds: bin-major kernel)
-    const int64_t half = KS / 2;
-    hf_prep_mma_kernel<<<(unsigned)((ld * half + 255) / 256), 256, 0, st>>>(pl, plan->w, ld, KS);
-    plan->launches++;
     const dim3 grid((unsigned)(ld / MM));
     if (const int rc_tab = upload_logtab()) return rc_tab;
     long long* trace = nullptr;

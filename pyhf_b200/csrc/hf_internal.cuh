@@ -88,7 +88,6 @@ struct Work {
     double* GsegT;  // [S*NSEG][ld]  sum_{b in seg} w_b r_{s,b}
     double* gradT;  // [P][ld]
     double* mainv;  // [ld]          main-term partial sums
-    double* coefK;  // [ld][KS]      DMMA path: point-major histosys coefficients (c1_h, c2_h interleaved)
     double* dconst; // [data_rows]   -sum lgamma(n+1) - sum ln(sigma sqrt(2pi)) ... (theta-independent)
 };
 
