@@ -120,6 +120,12 @@ __device__ __forceinline__ double pois_term_fast(double n, double lam, const dou
     return xl - lam;
 }
 
+// A operand of the forward product in shared memory: element (column k, point p) of the CTA's
+// coefficient block.  Column-major with the 16 point PAIRS of a column XOR-swizzled by the column, so
+// that one 16-byte load gives a lane the A fragments of two m-tiles (points 2g, 2g+1) and the four
+// columns k4*4 + t of a quarter warp fall into different banks.
+__device__ __forceinline__ int coef_at(int k, int p) { return k * MM + ((((p >> 1) ^ (2 * (k & 3))) << 1) | (p & 1)); }
+
 __device__ __forceinline__ double cell_factor(const DevPlan& pl, const Work& w, int64_t ld, int64_t p,
                                               int s, int bb, int seg, double& bfprod) {
     bfprod = 1.0;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(NTHR, 1)
 hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __restrict__ data,
                    int per_point, const int* __restrict__ row_idx, int KS, long long* trace, int ltab_off) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* coefs = reinterpret_cast<double*>(smem_raw);            // [MM][KS]
+    double* coefs = reinterpret_cast<double*>(smem_raw);            // [KS][MM] column-major, pairs of points swizzled (coef_at)
     double* tbuf_all = coefs + (size_t)MM * KS;                      // [2 halves][NSTAGE][KC*CSH]
     double* wfs = tbuf_all + 2 * NSTAGE * KC * CSH;                  // [MM][CS]  Delta, then w*F
     uint64_t* bars_all = reinterpret_cast<uint64_t*>(wfs + MM * CS); // per half: full[NSTAGE] | empty[NSTAGE]
@@ -273,7 +279,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             double d1, d2;
             hf_hs_coeffs(pl.hs_code, w.parsT[(int64_t)pl.hs_par[h] * ld + pt0 + pt], v.x, v.y, d1, d2);
         }
-        *reinterpret_cast<double2*>(&coefs[(size_t)pt * KS + 2 * h]) = v;
+        coefs[coef_at(2 * h, pt)] = v.x;
+        coefs[coef_at(2 * h + 1, pt)] = v.y;
     }
     __syncthreads();
 
@@ -293,7 +300,6 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     int gseg = -1;
 #pragma unroll
     for (int s = 0; s < NPOS; ++s) gacc[s] = fseg[s] = 0.0;
-    const int ra = 2 * (t & 1);
 
     for (int tile = 0; tile < ntiles; ++tile) {
         // HF_MMA_TRACE: phase time stamps of the first CTA, [half][tile][forward, epilogue, backward, end]
@@ -310,15 +316,18 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             for (int chunk = 0; chunk < NCH; ++chunk) {
                 issue_next();
                 mbar_wait(&bars[consumed % NSTAGE], (consumed / NSTAGE) & 1);
-                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + 16 * hw + g;
-                const double* ca = coefs + (size_t)g * KS + chunk * KC + t;
+                // m-tile mi, row g = point 16*(mi>>1) + 2g + (mi&1); n-tile ni, column n = cell 2n + ni of
+                // the warp's 16: three 16-byte loads feed the eight DMMA of a k-step
+                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + 16 * hw + 2 * g;
+                const double* ca = coefs + (size_t)(chunk * KC + t) * MM;  // column chunk*KC + k4*4 + t: (k & 3) == t
+                const int sw0 = ((g ^ (2 * t)) << 1), sw1 = (((8 + g) ^ (2 * t)) << 1);
 #pragma unroll
                 for (int k4 = 0; k4 < KC / 4; ++k4) {
-                    double a[4], b[2];
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) a[mi] = ca[(size_t)(8 * mi) * KS + k4 * 4];
-#pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) b[ni] = tb[(k4 * 4 + t) * CSH + 8 * ni];
+                    const double2 a01 = *reinterpret_cast<const double2*>(ca + k4 * 4 * MM + sw0);
+                    const double2 a23 = *reinterpret_cast<const double2*>(ca + k4 * 4 * MM + sw1);
+                    const double2 b01 = *reinterpret_cast<const double2*>(tb + (k4 * 4 + t) * CSH);
+                    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                    const double b[2] = {b01.x, b01.y};
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -330,20 +339,20 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 if (lane == 0) mbar_arrive(&bars[NSTAGE + consumed % NSTAGE]);
                 ++consumed;
             }
-            // Delta fragments -> shared [point][cell]; lane owns point 8mi+g, bin 4*warp+2ni+(t>>1),
-            // rows ra, ra+1 of every (mi, ni) tile.  The cells still hold w*F of the previous tile
-            // until every warp of the half has left its backward product.
+            // Delta fragments -> shared [point][cell]; with the tile mapping above a lane owns, per
+            // m-tile, all four rows of bin 4*warp + t of one point (row = 2j + ni).  The cells still hold
+            // w*F of the previous tile until every warp of the half has left its backward product.
             half_barrier(half);
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {
-                    double2 st;
-                    st.x = facc[mi][ni][0];
-                    st.y = facc[mi][ni][1];
-                    const int bl = 4 * warp + 2 * ni + (t >> 1);
-                    *reinterpret_cast<double2*>(&wfs[(size_t)(8 * mi + g) * CS + 4 * bl + ra]) = st;
-                }
+            for (int mi = 0; mi < 4; ++mi) {
+                double4 st;
+                st.x = facc[mi][0][0];
+                st.y = facc[mi][1][0];
+                st.z = facc[mi][0][1];
+                st.w = facc[mi][1][1];
+                const int pt = 16 * (mi >> 1) + 2 * g + (mi & 1);
+                *reinterpret_cast<double4*>(&wfs[(size_t)pt * CS + 4 * (4 * warp + t)]) = st;
+            }
         }
         // ---- the tile's model constants were requested after the previous epilogue: make them and
         //      the Delta tile visible
@@ -592,8 +601,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 if (h < pl.H) {
                     const int par = pl.hs_par[h];
                     // alpha of (point, modifier) from the coefficient block: c1 (code4p), c1 + c2 (code0)
-                    const double2 cc = *reinterpret_cast<const double2*>(&coefs[(size_t)(8 * hw + g) * KS + 2 * h]);
-                    const double alpha = (pl.hs_code == HF_HS_CODE4P) ? cc.x : cc.x + cc.y;
+                    const double c1s = coefs[coef_at(2 * h, 8 * hw + g)], c2s = coefs[coef_at(2 * h + 1, 8 * hw + g)];
+                    const double alpha = (pl.hs_code == HF_HS_CODE4P) ? c1s : c1s + c2s;
                     double c1, c2, d1, d2;
                     hf_hs_coeffs(pl.hs_code, alpha, c1, c2, d1, d2);
                     atomicAdd(&w.gradT[(int64_t)par * ld + pw],
