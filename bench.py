@@ -504,7 +504,7 @@ def run_b200(args):
     achieved_tf = FLOP_PER_EVAL * B / (main_avg_ms * 1e-3) / 1e12
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["hf_main_mma_kernel_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["hf_main_mma_kernel_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
     roofline = {
