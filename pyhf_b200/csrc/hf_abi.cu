@@ -299,6 +299,20 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
     for (int q = 0; q < S * NSEG; ++q) dp.max_sf_q = std::max(dp.max_sf_q, d->sf_ptr[q + 1] - d->sf_ptr[q]);
     for (int pp = 0; pp < P; ++pp) dp.max_sf_par = std::max(dp.max_sf_par, sfp_ptr[pp + 1] - sfp_ptr[pp]);
     dp.mma_ok = mma_ok ? 1 : 0; dp.mma_ntiles = mma_ntiles; dp.mma_nchunks = mma_nchunks;
+    {
+        std::vector<int> seen(P, 0);
+        dp.mma_hs_unique = 1;
+        for (int h = 0; h < H; ++h)
+            if (seen[d->hs_par[h]]++) dp.mma_hs_unique = 0;
+        std::vector<int> bin_of(P, -1);
+        dp.mma_bf_unique = 1;
+        for (size_t i = 0; i < (size_t)K * S * NB; ++i) {
+            const int q = d->bf_par[i], b = (int)(i % NB);
+            if (q < 0) continue;
+            if (bin_of[q] >= 0 && bin_of[q] != b) dp.mma_bf_unique = 0;
+            bin_of[q] = b;
+        }
+    }
     dp.mma_nother = n_other; dp.mma_other[0] = other[0]; dp.mma_other[1] = other[1];
     dp.mma_tt = DP(double, o_tt);
     dp.ah_ok = ah_ok ? 1 : 0; dp.ah_nsfp = (int)sfp_list.size(); dp.ah_nbl = (int)bl_par.size();

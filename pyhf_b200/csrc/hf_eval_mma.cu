@@ -489,8 +489,11 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                         double4 st;  // A' operand of the backward product
                         st.x = wf[0]; st.y = wf[1]; st.z = wf[2]; st.w = wf[3];
                         *reinterpret_cast<double4*>(cell) = st;
-                        if (WG && gpar[j] >= 0 && wgt[j] != 0.0)
-                            atomicAdd(&w.gradT[(int64_t)gpar[j] * ld + p], wgt[j] * gsum);
+                        if (WG && gpar[j] >= 0 && wgt[j] != 0.0) {
+                            // (a parameter that acts on this bin only: this is the row's one contribution)
+                            if (pl.mma_bf_unique) w.gradT[(int64_t)gpar[j] * ld + p] = wgt[j] * gsum;
+                            else atomicAdd(&w.gradT[(int64_t)gpar[j] * ld + p], wgt[j] * gsum);
+                        }
                     }
                 }
             }
@@ -583,7 +586,15 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     }
 
     // ---------------------------------------------------------------- flush
-    atomicAdd(&w.mainv[p], val);  // the eight warps hold different bins of the same points
+    // The eight warps hold different bins of the same points, the two halves partial sums over
+    // different cells of the same (point, column): both are combined through the table buffers of
+    // the half (free now: every chunk requested has been consumed) instead of atomics on global
+    // memory, so the main term and the histosys gradients leave as plain stores.
+    double* xch = tbuf;                                  // [NCH][NT_BWD][2][4 warps][32 lanes] of this half
+    double* vals = tbuf + NCH * NT_BWD * 2 * HTHR;       // [4 warps][32 lanes]
+    const double* xch_other = tbuf_all + (size_t)(1 - half) * NSTAGE * KC * CSH;
+    half_barrier(half);  // every warp of the half is done with the last table chunk
+    vals[hw * 32 + lane] = val;
     if (GRAD) {
         if (gseg >= 0) {
 #pragma unroll
@@ -591,22 +602,50 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 if (pos_smp[q] >= 0 && gacc[q] != 0.0)
                     atomicAdd(&w.GsegT[((int64_t)pos_smp[q] * pl.NSEG + gseg) * ld + p], gacc[q]);
         }
-        // bacc[chunk][ni] = C'[point 8*warp+g][k = chunk*KC + 8ni + 2t, +1] = (T1, T2) sums of one modifier
-        const int64_t pw = pt0 + 8 * (warp & 3) + g;  // the two cell halves add their partial sums
+        // chunk c is finished by half (c & 1): the other half hands its partial sums over
 #pragma unroll
         for (int chunk = 0; chunk < NCH; ++chunk)
+            if ((chunk & 1) != half) {
 #pragma unroll
-            for (int ni = 0; ni < NT_BWD; ++ni) {
-                const int h = (chunk * KC + 8 * ni + 2 * t) >> 1;
-                if (h < pl.H) {
-                    const int par = pl.hs_par[h];
-                    // alpha of (point, modifier) from the coefficient block: c1 (code4p), c1 + c2 (code0)
-                    const double c1s = coefs[coef_at(2 * h, 8 * hw + g)], c2s = coefs[coef_at(2 * h + 1, 8 * hw + g)];
-                    const double alpha = (pl.hs_code == HF_HS_CODE4P) ? c1s : c1s + c2s;
-                    double c1, c2, d1, d2;
-                    hf_hs_coeffs(pl.hs_code, alpha, c1, c2, d1, d2);
-                    atomicAdd(&w.gradT[(int64_t)par * ld + pw],
-                              d1 * bacc[chunk][ni][0] + d2 * bacc[chunk][ni][1]);
+                for (int ni = 0; ni < NT_BWD; ++ni) {
+                    xch[((chunk * NT_BWD + ni) * 2 + 0) * HTHR + htid] = bacc[chunk][ni][0];
+                    xch[((chunk * NT_BWD + ni) * 2 + 1) * HTHR + htid] = bacc[chunk][ni][1];
+                }
+            }
+    }
+    __syncthreads();
+    if (warp == 0) {  // (constraint terms and constants: hf_finish_value_kernel, at full occupancy --
+                      //  folded into this kernel they sat on every CTA's critical path: +0.2 ms per step)
+        double v = 0.0;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int ww = 0; ww < HTHR / 32; ++ww)
+                v += (tbuf_all + (size_t)hh * NSTAGE * KC * CSH + NCH * NT_BWD * 2 * HTHR)[ww * 32 + lane];
+        w.mainv[p] = v;
+    }
+    if (GRAD) {
+        // bacc[chunk][ni] = C'[point 8*hw+g][k = chunk*KC + 8ni + 2t, +1] = (T1, T2) sums of one modifier
+        const int64_t pw = pt0 + 8 * hw + g;
+#pragma unroll
+        for (int chunk = 0; chunk < NCH; ++chunk)
+            if ((chunk & 1) == half) {
+#pragma unroll
+                for (int ni = 0; ni < NT_BWD; ++ni) {
+                    const int h = (chunk * KC + 8 * ni + 2 * t) >> 1;
+                    if (h < pl.H) {
+                        const int par = pl.hs_par[h];
+                        // alpha of (point, modifier) from the coefficient block: c1 (code4p), c1 + c2 (code0)
+                        const double c1s = coefs[coef_at(2 * h, 8 * hw + g)], c2s = coefs[coef_at(2 * h + 1, 8 * hw + g)];
+                        const double alpha = (pl.hs_code == HF_HS_CODE4P) ? c1s : c1s + c2s;
+                        double c1, c2, d1, d2;
+                        hf_hs_coeffs(pl.hs_code, alpha, c1, c2, d1, d2);
+                        const double s0 = bacc[chunk][ni][0] + xch_other[((chunk * NT_BWD + ni) * 2 + 0) * HTHR + htid];
+                        const double s1 = bacc[chunk][ni][1] + xch_other[((chunk * NT_BWD + ni) * 2 + 1) * HTHR + htid];
+                        const double gh = d1 * s0 + d2 * s1;
+                        if (pl.mma_hs_unique) w.gradT[(int64_t)par * ld + pw] = gh;  // the row's only writer
+                        else atomicAdd(&w.gradT[(int64_t)par * ld + pw], gh);
+                    }
                 }
             }
     }

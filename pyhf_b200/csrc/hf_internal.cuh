@@ -49,6 +49,8 @@ struct DevPlan {
     int mma_ok;                  // plan fits the tensor-core kernel (0 < H, R <= 4, <= 2 other samples)
     int mma_ntiles;              // bin tiles of HF_MMA_BT bins
     int mma_nchunks;             // K chunks of HF_MMA_KC columns (column 2h = T1_h, 2h+1 = T2_h)
+    int mma_hs_unique;           // every histosys modifier has its own parameter (plain gradient stores)
+    int mma_bf_unique;           // every per-bin parameter acts on exactly one bin (plain gradient stores)
     int mma_nother;              // samples without histosys
     int mma_other[2];            // their sample indices
     const double* mma_tt;        // [ntiles][2 halves][nchunks][HF_MMA_KC][HF_MMA_CSH] (cell = (bin_local % 16)*4 + row)
