@@ -489,8 +489,9 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
     // i-1 overlap (PCIe is full duplex); the copy streams are ordered against `st` by events.
     // Chunks are whole waves of the dominant kernel (one CTA of HF_MMA_M points per SM and wave:
     // a 16384-point chunk would be 3.46 waves on 148 SMs and pay for 4).  The first upload and the
-    // last download cannot overlap anything, so the schedule ramps 1, 2, 3, 3, ... waves and ends
-    // with a single wave.
+    // last download cannot overlap anything, so the schedule ramps up from one wave and down to one
+    // wave (below; C4, 65 536 points: 1, 3, 6.84, 2, 1 waves = 10.75 ms against 11.02 ms for
+    // 1, 2, 3, 3, 3, 0.84, 1 and 9.73 ms for the kernels alone).
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -513,13 +514,39 @@ int hf_logpdf_grad_host(hf_plan* plan, const double* pars_host, const double* da
     }
     std::vector<int64_t> ch_b0, ch_nb;
     {
-        int64_t b0 = 0, left = B - WAVE;  // the closing single wave is set aside
-        for (int k = 0; left > 0; ++k) {
-            const int64_t nb = std::min<int64_t>(left, WAVE * std::min(k + 1, 3));
+        // Waves per chunk: ramp up (the upload of chunk i+1 has to fit under the kernels of chunk i: an
+        // upload or download takes ~0.3 of the kernel time of the same points), a steady size, ramp
+        // down (the download of chunk i has to fit under the kernels of chunk i+1; the last download is
+        // exposed, so the last chunk is one wave).  HF_E2E_SCHED="1,3;8;2,1" overrides head;steady;tail.
+        std::vector<int> head = {1, 3}, tail = {2, 1};
+        int steady = 8;
+        if (const char* e = getenv("HF_E2E_SCHED")) {
+            std::vector<int> part[3];
+            int k = 0;
+            for (const char* q = e; *q && k < 3;) {
+                if (*q == ';') { ++k; ++q; continue; }
+                if (*q == ',') { ++q; continue; }
+                const int v = atoi(q);
+                if (v > 0) part[k].push_back(v);
+                while (*q && *q != ',' && *q != ';') ++q;
+            }
+            if (!part[0].empty() && !part[1].empty() && !part[2].empty()) {
+                head = part[0]; steady = part[1][0]; tail = part[2];
+            }
+        }
+        int64_t tail_pts = 0;
+        for (int v : tail) tail_pts += WAVE * v;
+        int64_t b0 = 0, left = B - tail_pts;  // the closing chunks are set aside
+        for (size_t k = 0; left > 0; ++k) {
+            const int64_t nb = std::min<int64_t>(left, WAVE * (k < head.size() ? head[k] : steady));
             ch_b0.push_back(b0); ch_nb.push_back(nb);
             b0 += nb; left -= nb;
         }
-        ch_b0.push_back(b0); ch_nb.push_back(B - b0);
+        for (size_t k = 0; k < tail.size() && b0 < B; ++k) {
+            const int64_t nb = (k + 1 == tail.size()) ? B - b0 : std::min<int64_t>(B - b0, WAVE * tail[k]);
+            ch_b0.push_back(b0); ch_nb.push_back(nb);
+            b0 += nb;
+        }
     }
     const int64_t nch = (int64_t)ch_b0.size();
     std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);

@@ -233,11 +233,11 @@ def test_host_buffer_entry_point(golden, cuda):
     assert (np.abs(grad.numpy() - g["grad"]) / scale).max() < 1e-10
 
 
-@pytest.mark.parametrize("B", [28417, 40001])
+@pytest.mark.parametrize("B", [28417, 40001, 70001])
 def test_host_buffer_entry_point_pipelined(B, golden, cuda):
     """above two 3-wave chunks the host entry pipelines H2D / kernels / D2H over a ramped chunk
-    schedule (1, 2, 3, 3, ... waves and a closing single wave; ragged here): every point must come
-    back in its own slot, equal to the device-resident call"""
+    schedule (1, 3, 8, 8, ... waves up, 2 and 1 waves down; ragged here, 70001 points have a steady
+    chunk in the middle): every point must come back in its own slot, equal to the device-resident call"""
     g = golden("mixed_code4p_code4")
     hp = g.host_plan()
     plan = _dev_plan(g, cuda)
