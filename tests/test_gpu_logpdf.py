@@ -289,3 +289,60 @@ def test_tensor_core_path_on_small_models(name, B, golden, cuda, monkeypatch):
         sc = np.max(np.abs(g_ref), axis=1, keepdims=True) + 1e-300
         assert (np.abs(gr - g_ref) / sc).max() < 1e-10
     assert torch.allclose(v1s, v0s, rtol=1e-12, atol=1e-10)
+
+
+def _spec_two_channels(nb, staterror, shared_shapefactor, shapesys):
+    """histosys on every background + per-bin factors in the three forms the DMMA epilogue
+    distinguishes: one parameter per bin (interleaved path, plain gradient store), one parameter on a
+    bin of EACH channel (shapefactor shared by name: atomic adds), two per-bin kinds on one bin (general path)"""
+    rng = np.random.default_rng(5)
+    channels = []
+    for c in range(2):
+        samples = [{"name": "signal", "data": rng.uniform(1, 10, nb).round(3).tolist(),
+                    "modifiers": [{"name": "mu", "type": "normfactor", "data": None}]}]
+        for s in range(2):
+            nom = rng.uniform(20, 200, nb).round(3)
+            mods = [{"name": f"hs{k}", "type": "histosys",
+                     "data": {"hi_data": (nom * (1 + rng.uniform(0, 0.08, nb))).round(3).tolist(),
+                              "lo_data": (nom * (1 - rng.uniform(0, 0.08, nb))).round(3).tolist()}} for k in range(3)]
+            mods.append({"name": "ns0", "type": "normsys", "data": {"hi": 1.05 + 0.01 * s, "lo": 0.94}})
+            if staterror:
+                mods.append({"name": f"stat_ch{c}", "type": "staterror", "data": (0.3 * np.sqrt(nom)).round(3).tolist()})
+            if shared_shapefactor and s == 0:
+                mods.append({"name": "sf_shared", "type": "shapefactor", "data": None})
+            if shapesys and s == 1:
+                mods.append({"name": f"shape_ch{c}", "type": "shapesys", "data": (0.1 * nom).round(3).tolist()})
+            samples.append({"name": f"bkg{s}", "data": nom.tolist(), "modifiers": mods})
+        channels.append({"name": f"ch{c}", "samples": samples})
+    return {"channels": channels}
+
+
+@pytest.mark.parametrize("staterror,shared_shapefactor,shapesys",
+                         [(True, False, False), (False, True, False), (True, False, True), (True, True, True), (False, False, True)])
+def test_dmma_epilogue_per_bin_factor_forms(staterror, shared_shapefactor, shapesys, cuda):
+    """every way a per-bin parameter can reach the gradient in hf_main_mma_kernel (plain store for a
+    parameter of one bin, RED when a parameter acts on bins of two channels, the general path when a bin
+    carries two per-bin kinds) against the numpy oracle, B = 512 points, 40 bins per channel (tiles
+    that mix the forms)"""
+    from oracle import hf_oracle as O
+    from pyhf_b200.batched import DevicePlan
+    from pyhf_b200.compile import compile_spec
+
+    hp = compile_spec(_spec_two_channels(40, staterror, shared_shapefactor, shapesys), poi_name="mu")
+    op = O.Plan(hp.arrays())
+    plan = DevicePlan(hp, cuda)
+    rng = np.random.default_rng(17)
+    free = ~hp.fixed.astype(bool)
+    lam0 = O.expected_data(op, hp.init[None])[0]
+    data = np.concatenate([rng.poisson(lam0[:hp.n_bins]), hp.auxdata]).astype(float)
+    data[3] = 0.0  # an empty bin: w = -1 exactly
+    x = hp.init[None] + rng.normal(0, 0.3, (512, hp.n_pars)) * free[None]
+    x = np.clip(x, hp.lo + 1e-3, hp.hi - 1e-3)
+    v_ref, g_ref = O.logpdf_grad(op, x, data)
+    v, g = plan.logpdf_grad(x, data)
+    v, g = v.cpu().numpy(), g.cpu().numpy()
+    assert np.isfinite(v_ref).all()
+    np.testing.assert_allclose(v, v_ref, rtol=1e-12, atol=1e-11)
+    sc = np.max(np.abs(g_ref), axis=1, keepdims=True)
+    assert (np.abs(g - g_ref) / sc).max() < 1e-10
+    np.testing.assert_allclose(plan.logpdf(x, data).cpu().numpy(), v_ref, rtol=1e-12, atol=1e-11)
