@@ -269,7 +269,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     };
     for (int i = 0; i < NSTAGE - 1; ++i) issue_next();  // prologue: NSTAGE-1 chunks in flight
     // A operand of the forward product: the histosys coefficients (c1_h, c2_h) of the CTA's 32 points,
-    // point-major rows of KS doubles (zero padded), computed here from the batch-major parameters
+    // KS columns (zero padded) in the layout of coef_at, computed here from the batch-major parameters
     // (lanes = consecutive points: coalesced reads) instead of travelling through a global scratch
     for (int i = tid; i < (KS / 2) * MM; i += NTHR) {
         const int h = i / MM, pt = i - h * MM;
@@ -292,7 +292,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
 #pragma unroll
             for (int n = 0; n < NT_BWD; ++n) bacc[c][n][0] = bacc[c][n][1] = 0.0;
     }
-    // epilogue state: thread = point `lane`, warp = 8 consecutive bins of every tile
+    // epilogue state: thread = point `lane`, warp = 4 consecutive bins of every tile
     const int64_t p = pt0 + lane;
     double val = 0.0;      // main-term partial sum of this point over this warp's bins
     double gacc[NPOS];     // per-sample sums of w*bf*base inside the current segment
