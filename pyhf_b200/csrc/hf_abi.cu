@@ -150,7 +150,7 @@ int hf_plan_create(const hf_plan_desc* d, hf_plan** out) {
                     for (int which = 0; which < 2; ++which) {
                         const int k = 2 * h + which, chunk = k / HF_MMA_KC, kl = k % HF_MMA_KC;
                         const double v = (which ? d->hs_t2 : d->hs_t1)[((size_t)h * R + r) * NB + b];
-                        tt[((((size_t)tile * 2 + half) * mma_nchunks + chunk) * HF_MMA_KC + kl) * HF_MMA_CSH + cell] = v;
+                        tt[(((size_t)tile * 2 + half) * mma_nchunks + chunk) * HF_MMA_KC * HF_MMA_CSH + HF_MMA_ROW(kl) + cell] = v;
                     }
                 }
     }

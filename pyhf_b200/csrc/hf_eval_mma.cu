@@ -175,8 +175,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
     int64_t* row_off = reinterpret_cast<int64_t*>(bars_all + 16);    // [MM]
     // tile constants: those of tile i+1 are requested (cp.async) when the epilogue of tile i is done
     // and land during the two products that follow
-    double* nd_s = reinterpret_cast<double*>(row_off + MM);          // [MM][BT+1] observed counts
-    double* nom_s = nd_s + MM * (BT + 1);                            // [S][BT]    nominal of the tile
+    double* nom_s = reinterpret_cast<double*>(row_off + MM);         // [S][BT]    nominal of the tile
     int* seg_s = reinterpret_cast<int*>(nom_s + SMAX * BT);          // [BT]
     int* srow_s = seg_s + BT;                                        // [SMAX]     histosys row of a sample
     int* bf_s = srow_s + SMAX;                                       // [K][S][BT] per-bin factor indices
@@ -242,12 +241,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             cp_async4(&bf_s[ks * BT + bl], &pl.bf_par[(int64_t)ks * pl.NB + min(b0 + bl, pl.NB - 1)]);
         }
         if (htid < HB) cp_async4(&seg_s[hb0 + htid], &pl.bin_seg[min(b0 + hb0 + htid, pl.NB - 1)]);
-        // observed counts of the 32 points: a warp reads 16 bins of two points per pass
-        for (int q = 2 * hw + (lane >> 4); q < MM; q += 2 * (HTHR / 32)) {
-            const int bl = hb0 + (lane & 15);
-            cp_async8(&nd_s[q * (BT + 1) + bl], &data[row_off[q] + min(b0 + bl, pl.NB - 1)]);
-        }
     };
+    const double* drow = data + row_off[lane];  // observed counts of this lane's point (epilogue: lane = point)
     prefetch_tile(0);
     int issued = 0;    // table chunks of this half requested so far (uniform within the half)
     int consumed = 0;  // table chunks of this half consumed so far (uniform within the half)
@@ -318,7 +313,8 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 mbar_wait(&bars[consumed % NSTAGE], (consumed / NSTAGE) & 1);
                 // m-tile mi, row g = point 16*(mi>>1) + 2g + (mi&1); n-tile ni, column n = cell 2n + ni of
                 // the warp's 16: three 16-byte loads feed the eight DMMA of a k-step
-                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + 16 * hw + 2 * g;
+                // (row k4*4 + t of the chunk: HF_MMA_ROW puts a lane-constant 4*(t>>1) on top of the stride)
+                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + 16 * hw + 2 * g + 4 * (t >> 1);
                 const double* ca = coefs + (size_t)(chunk * KC + t) * MM;  // column chunk*KC + k4*4 + t: (k & 3) == t
                 const int sw0 = ((g ^ (2 * t)) << 1), sw1 = (((8 + g) ^ (2 * t)) << 1);
 #pragma unroll
@@ -359,6 +355,11 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
         cp_async_wait_all();
         half_barrier(half);
         if (tr) trace[(half * ntiles + tile) * 4 + 1] = clock64();
+        // observed counts of this point on the warp's 4 bins: straight from global memory (L2), in
+        // flight while the rates are formed -- staging them cost 8 KB of shared memory
+        double nd4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nd4[j] = drow[min(tile * BT + 4 * warp + j, NB - 1)];
 
         // ---------------------------------------------------------------- epilogue
         // positions 0..3 are the histosys rows (Delta in cell[0..3]), 4..7 the other samples.
@@ -454,7 +455,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 for (int j = 0; j < 4; ++j) {
                     const int bl = 4 * warp + j;
                     const bool valid = (tile * BT + bl < NB) && act[j];
-                    const double n = nd_s[lane * (BT + 1) + bl];
+                    const double n = nd4[j];
                     if (valid) val += pois_term_fast(n, lam[j], ltab);
                     // n * rcp(lambda) (correctly rounded reciprocal + one FMA) instead of the IEEE divide:
                     // <= 1.5 ulp on n/lambda, same inf / NaN behaviour at lambda = 0
@@ -532,7 +533,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     lam = fma(fseg[q] * bfv[q], basev[q], lam);
                 }
             }
-            const double n = nd_s[lane * (BT + 1) + bl];
+            const double n = drow[bb];
             if (valid) val += hf_pois_term(n, lam);
             if (GRAD) {
                 const double wgt = valid ? ((n == 0.0) ? -1.0 : n / lam - 1.0) : 0.0;
@@ -565,17 +566,22 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             for (int chunk = 0; chunk < NCH; ++chunk) {
                 issue_next();
                 mbar_wait(&bars[consumed % NSTAGE], (consumed / NSTAGE) & 1);
-                // warp = (m-tile: points 8*hw+g) x (the half's 64 cells)
-                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + (size_t)g * CSH + t;
-                const double* arow = wfs + (size_t)(8 * hw + g) * CS + t + NCH_CELLS * half;
+                // warp = (m-tile: points 8*hw+g) x (the half's 64 cells).  The k dimension of a DMMA is
+                // four cells in any order both operands agree on: k-step 2j + e takes cells 8j + 2t + e, so
+                // one 16-byte load per operand feeds two k-steps (6 loads per 10 DMMA instead of 12)
+                const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + HF_MMA_ROW(g) + 2 * t;
+                const double* arow = wfs + (size_t)(8 * hw + g) * CS + 2 * t + NCH_CELLS * half;
 #pragma unroll
-                for (int c4 = 0; c4 < NCH_CELLS / 4; ++c4) {
-                    const double a = arow[4 * c4];
+                for (int j = 0; j < NCH_CELLS / 8; ++j) {
+                    const double2 a = *reinterpret_cast<const double2*>(arow + 8 * j);
+                    double2 b[NT_BWD];
 #pragma unroll
-                    for (int ni = 0; ni < NT_BWD; ++ni) {
-                        const double b = tb[(size_t)(8 * ni) * CSH + 4 * c4];
-                        dmma884(bacc[chunk][ni][0], bacc[chunk][ni][1], a, b);
-                    }
+                    for (int ni = 0; ni < NT_BWD; ++ni)
+                        b[ni] = *reinterpret_cast<const double2*>(tb + (size_t)(8 * ni) * CSH + 8 * j);
+#pragma unroll
+                    for (int ni = 0; ni < NT_BWD; ++ni) dmma884(bacc[chunk][ni][0], bacc[chunk][ni][1], a.x, b[ni].x);
+#pragma unroll
+                    for (int ni = 0; ni < NT_BWD; ++ni) dmma884(bacc[chunk][ni][0], bacc[chunk][ni][1], a.y, b[ni].y);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[NSTAGE + consumed % NSTAGE]);
@@ -674,7 +680,7 @@ int launch(hf_plan* plan, int64_t B, int64_t ld, const double* data, int per_poi
     const DevPlan& pl = plan->d;
     const int KS = hf_mma_ks(pl.H);
     size_t smem = sizeof(double) * ((size_t)MM * KS + 2 * NSTAGE * KC * CSH + MM * CS) + 128 + 8 * MM + 128 +
-                  sizeof(double) * (MM * (BT + 1) + SMAX * BT) +
+                  sizeof(double) * (SMAX * BT) +
                   sizeof(int) * (BT + SMAX + (size_t)pl.K * pl.S * BT) + 64;
     smem = (smem + 15) / 16 * 16;
     const int ltab_off = (int)smem;

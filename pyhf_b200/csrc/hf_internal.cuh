@@ -53,7 +53,7 @@ struct DevPlan {
     int mma_bf_unique;           // every per-bin parameter acts on exactly one bin (plain gradient stores)
     int mma_nother;              // samples without histosys
     int mma_other[2];            // their sample indices
-    const double* mma_tt;        // [ntiles][2 halves][nchunks][HF_MMA_KC][HF_MMA_CSH] (cell = (bin_local % 16)*4 + row)
+    const double* mma_tt;        // [ntiles][2 halves][nchunks][HF_MMA_KC rows at HF_MMA_ROW][64 cells] (cell = (bin_local % 16)*4 + row)
     // ---- analytic Hessian (hf_hess_analytic.cu)
     int ah_ok;                   // plan qualifies (else the minimiser differences the analytic gradient)
     int ah_nsfp;                 // distinct parameters among the scalar-factor entries
@@ -74,7 +74,11 @@ struct DevPlan {
 #define HF_MMA_NC 128   // cells per tile (4 rows per bin)
 #define HF_MMA_CS 132   // padded cell stride: == 4 mod 16 doubles -> conflict-free fragment loads
 #define HF_MMA_NCH 64   // cells of a half tile (16 bins): the unit one half of the CTA (4 warps) works on
-#define HF_MMA_CSH 68   // padded cell stride of a half-tile table chunk (== 4 mod 16 doubles)
+#define HF_MMA_CSH 72   // row stride of a half-tile table chunk (== 8 mod 16 doubles); row r starts at HF_MMA_ROW(r)
+// Row r of a table chunk starts at r*72 + 4*((r>>1)&1) doubles: the four rows k4*4 + t of a forward
+// k-step then sit at bank offsets {0, 8, 4, 12} and the two rows 8ni + g, g in {0, 1}, of a backward
+// quarter warp at {0, 8}, so the 16-byte fragment loads of BOTH products are conflict-free.
+#define HF_MMA_ROW(r) ((r) * HF_MMA_CSH + 4 * (((r) >> 1) & 1))
 #define HF_MMA_KC 40    // K columns per chunk (20 modifiers)
 #define HF_MMA_M 32     // parameter points per CTA
 
