@@ -18,7 +18,7 @@
 //            accumulators stay in registers over all bin tiles, flushed once per CTA
 // The CTA is two independent HALVES of 4 warps: half h owns bins 16h .. 16h+15 of every tile
 // (cells 64h .. 64h+63) through all three phases, with its own stream of table chunks
-// [40][68] (21 KB, double buffered, bulk copies + mbarriers), its own tile constants and its own
+// of 40 rows (22.5 KB, three buffers, bulk copies + mbarriers), its own tile constants and its own
 // named barrier.  The epilogue is a latency chain (log, reciprocal) that leaves the fp64 pipe idle;
 // the halves are free to drift apart, so that one can be in its DMMA phases while the other is in
 // its epilogue (HF_MMA_TRACE=1 prints the phase time stamps of CTA 0).  Reference being replaced:
@@ -153,7 +153,7 @@ __device__ __forceinline__ void cell_bf_grad(const DevPlan& pl, const Work& w, i
 }
 
 constexpr int SMAX = 8;  // samples handled by the register-resident per-(sample, segment) sums
-// table-chunk buffers per half (21 KB each).  A half (one warp per scheduler) consumes a chunk in
+// table-chunk buffers per half (22.5 KB each).  A half (one warp per scheduler) consumes a chunk in
 // >= 1 280 cycles, a bulk copy takes ~2 500 from request to completion (HF_MMA_TRACE: with two
 // buffers the DMMA phases of a half ran at half the pipe rate, waiting for chunks), so two
 // chunks have to be in flight while the third is consumed
