@@ -68,3 +68,67 @@ def test_toy_batches_are_tagged_where_they_are_created():
             assert B200Optimizer._toy_batch_of(user[2], D) is None
     finally:
         pyhf.set_backend("numpy", "scipy")
+
+
+def test_dmma_table_row_layout_is_conflict_free_for_both_products():
+    """HF_MMA_ROW (csrc/hf_internal.cuh): rows of a table chunk sit at stride 72 doubles with a
+    4-double swizzle.  Shared memory serves a 16-byte load per quarter warp (8 lanes x 2 doubles = the
+    16 doubles = 32 banks of one wavefront), so a load is conflict-free iff its 8 lanes hit 8 different
+    2-double slots mod 16.  Forward product: lanes (g in {0,1}, t in 0..3) read row k4*4 + t, cells
+    2g, 2g+1; backward product: lanes read row 8ni + g, cells 8j + 2t, +1 -- for every quarter warp."""
+    import os
+    import re
+
+    src = open(os.path.join(os.path.dirname(__file__), "..", "pyhf_b200", "csrc", "hf_internal.cuh")).read()
+    csh = int(re.search(r"#define HF_MMA_CSH (\d+)", src).group(1))
+    kc = int(re.search(r"#define HF_MMA_KC (\d+)", src).group(1))
+    ncell = int(re.search(r"#define HF_MMA_NCH (\d+)", src).group(1))
+    assert "#define HF_MMA_ROW(r) ((r) * HF_MMA_CSH + 4 * (((r) >> 1) & 1))" in src
+
+    def row(r):
+        return r * csh + 4 * ((r >> 1) & 1)
+
+    # rows do not overlap and stay 16-byte aligned
+    for r in range(kc):
+        assert row(r) % 2 == 0 and row(r) + ncell <= (row(r + 1) if r + 1 < kc else kc * csh)
+
+    def slots(addrs):  # 2-double slots mod 16 doubles touched by a quarter warp
+        return sorted((a % 16) // 2 for a in addrs)
+
+    for quarter in range(4):  # lanes 8q .. 8q+7: g = lane >> 2, t = lane & 3
+        lanes = [(lane >> 2, lane & 3) for lane in range(8 * quarter, 8 * quarter + 8)]
+        for k4 in range(kc // 4):
+            for hw in range(4):
+                fwd = [row(4 * k4 + t) + 16 * hw + 2 * g for g, t in lanes]
+                assert slots(fwd) == list(range(8)), ("forward", quarter, k4, hw, slots(fwd))
+        for ni in range(kc // 8):
+            for j in range(ncell // 8):
+                bwd = [row(8 * ni + g) + 8 * j + 2 * t for g, t in lanes]
+                assert slots(bwd) == list(range(8)), ("backward", quarter, ni, j, slots(bwd))
+
+
+def test_dmma_coefficient_block_swizzle_is_conflict_free():
+    """coef_at (csrc/hf_eval_mma.cu): the forward product's A operand is column-major [k][32 points]
+    with the 16 point pairs of a column XOR-swizzled by 2*(k & 3); a lane (g, t) reads the pairs g and
+    8+g of column k4*4 + t with 16-byte loads -- every quarter warp must hit 8 different 2-double slots,
+    and the map must be a bijection on a column."""
+    import os
+
+    src = open(os.path.join(os.path.dirname(__file__), "..", "pyhf_b200", "csrc", "hf_eval_mma.cu")).read()
+    assert "return k * MM + ((((p >> 1) ^ (2 * (k & 3))) << 1) | (p & 1));" in src
+    MM = 32
+
+    def coef_at(k, p):
+        return k * MM + ((((p >> 1) ^ (2 * (k & 3))) << 1) | (p & 1))
+
+    for k in range(8):
+        assert sorted(coef_at(k, p) for p in range(MM)) == list(range(k * MM, (k + 1) * MM))
+    for quarter in range(4):
+        lanes = [(lane >> 2, lane & 3) for lane in range(8 * quarter, 8 * quarter + 8)]
+        for k4 in range(3):
+            for base_pair in (0, 8):  # m-tiles 0/1 and 2/3
+                addrs = [coef_at(4 * k4 + t, 2 * (base_pair + g)) for g, t in lanes]
+                assert all(a % 2 == 0 for a in addrs)
+                assert sorted((a % 16) // 2 for a in addrs) == list(range(8)), (quarter, k4, base_pair)
+                # the second element of the 16-byte load is the odd point of the pair
+                assert all(coef_at(4 * k4 + t, 2 * (base_pair + g) + 1) == a + 1 for (g, t), a in zip(lanes, addrs))
