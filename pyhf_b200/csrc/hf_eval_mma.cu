@@ -347,7 +347,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 st.z = facc[mi][0][1];
                 st.w = facc[mi][1][1];
                 const int pt = 16 * (mi >> 1) + 2 * g + (mi & 1);
-                *reinterpret_cast<double4*>(&wfs[(size_t)pt * CS + 4 * (4 * warp + t)]) = st;
+                *reinterpret_cast<double4*>(&wfs[HF_MMA_WFROW(pt) + 4 * (4 * warp + t)]) = st;
             }
         }
         // ---- the tile's model constants were requested after the previous epilogue: make them and
@@ -434,7 +434,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 for (int j = 0; j < 4; ++j) {
                     const int bl = 4 * warp + j;
                     act[j] = seg_s[bl] == seg_cur;
-                    const double4 dlt = *reinterpret_cast<const double4*>(wfs + (size_t)lane * CS + 4 * bl);
+                    const double4 dlt = *reinterpret_cast<const double4*>(wfs + HF_MMA_WFROW(lane) + 4 * bl);
                     const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
                     // positions without a sample carry fseg = 0 and read nominal row 0: no predicates
                     // (only the rarely used positions 5..7 keep a uniform guard)
@@ -467,7 +467,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                     for (int j = 0; j < 4; ++j) {
                         if (!act[j]) continue;  // warp-uniform
                         const int bl = 4 * warp + j;
-                        double* cell = wfs + (size_t)lane * CS + 4 * bl;
+                        double* cell = wfs + HF_MMA_WFROW(lane) + 4 * bl;
                         const double4 dlt = *reinterpret_cast<const double4*>(cell);
                         const double dl[4] = {dlt.x, dlt.y, dlt.z, dlt.w};
                         double wf[4];
@@ -510,7 +510,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
             const bool valid = b < NB;
             const int bb = valid ? b : NB - 1;
             const int seg = seg_s[bl];
-            double* cell = wfs + (size_t)lane * CS + 4 * bl;
+            double* cell = wfs + HF_MMA_WFROW(lane) + 4 * bl;
             if (seg != gseg) switch_segment(seg);  // warp-uniform: all lanes look at the same bin
             const double4 dlt = *reinterpret_cast<const double4*>(cell);
             double basev[NPOS], bfv[NPOS];
@@ -570,7 +570,7 @@ hf_main_mma_kernel(DevPlan pl, Work w, int64_t B, int64_t ld, const double* __re
                 // four cells in any order both operands agree on: k-step 2j + e takes cells 8j + 2t + e, so
                 // one 16-byte load per operand feeds two k-steps (6 loads per 10 DMMA instead of 12)
                 const double* tb = tbuf + (size_t)(consumed % NSTAGE) * KC * CSH + HF_MMA_ROW(g) + 2 * t;
-                const double* arow = wfs + (size_t)(8 * hw + g) * CS + 2 * t + NCH_CELLS * half;
+                const double* arow = wfs + HF_MMA_WFROW(8 * hw + g) + 2 * t + NCH_CELLS * half;
 #pragma unroll
                 for (int j = 0; j < NCH_CELLS / 8; ++j) {
                     const double2 a = *reinterpret_cast<const double2*>(arow + 8 * j);

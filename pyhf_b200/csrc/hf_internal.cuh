@@ -72,7 +72,12 @@ struct DevPlan {
 
 #define HF_MMA_BT 32    // bins per tile
 #define HF_MMA_NC 128   // cells per tile (4 rows per bin)
-#define HF_MMA_CS 132   // padded cell stride: == 4 mod 16 doubles -> conflict-free fragment loads
+#define HF_MMA_CS 136   // row stride of the Delta / w*F tile [point][128 cells]; row p starts at HF_MMA_WFROW(p)
+// Row p of the Delta / w*F tile starts at p*136 + 2*((p>>1)&3) doubles: eight consecutive rows then sit at
+// the eight different 2-double slots mod 16 (epilogue: lane = point, 16-byte accesses at one column), rows
+// 2m, 2m+1 eight doubles apart (A' operand of the backward product: lanes (g, t) read row 8hw+g, cells 8j+2t)
+// and rows p, p+2 two slots apart (Delta store: lanes (g, t) write rows 2g+m at column 4t).
+#define HF_MMA_WFROW(p) ((p) * HF_MMA_CS + 2 * (((p) >> 1) & 3))
 #define HF_MMA_NCH 64   // cells of a half tile (16 bins): the unit one half of the CTA (4 warps) works on
 #define HF_MMA_CSH 72   // row stride of a half-tile table chunk (== 8 mod 16 doubles); row r starts at HF_MMA_ROW(r)
 // Row r of a table chunk starts at r*72 + 4*((r>>1)&1) doubles: the four rows k4*4 + t of a forward

@@ -132,3 +132,41 @@ def test_dmma_coefficient_block_swizzle_is_conflict_free():
                 assert sorted((a % 16) // 2 for a in addrs) == list(range(8)), (quarter, k4, base_pair)
                 # the second element of the 16-byte load is the odd point of the pair
                 assert all(coef_at(4 * k4 + t, 2 * (base_pair + g) + 1) == a + 1 for (g, t), a in zip(lanes, addrs))
+
+
+def test_dmma_delta_tile_row_layout_is_conflict_free():
+    """HF_MMA_WFROW (csrc/hf_internal.cuh): rows of the Delta / w*F tile [32 points][128 cells] at stride
+    136 doubles with a 2-double swizzle.  Three access patterns, all 16-byte, must be conflict-free per
+    quarter warp: the epilogue (lane = point, one column), the A' fragments of the backward product
+    (lanes (g, t): row 8hw + g, cells 64h + 8j + 2t) and the Delta store (lanes (g, t): row
+    16(mi>>1) + 2g + (mi&1), column 4(4w + t))."""
+    import os
+    import re
+
+    src = open(os.path.join(os.path.dirname(__file__), "..", "pyhf_b200", "csrc", "hf_internal.cuh")).read()
+    cs = int(re.search(r"#define HF_MMA_CS (\d+)", src).group(1))
+    assert "#define HF_MMA_WFROW(p) ((p) * HF_MMA_CS + 2 * (((p) >> 1) & 3))" in src
+
+    def row(p):
+        return p * cs + 2 * ((p >> 1) & 3)
+
+    for p in range(32):
+        assert row(p) % 2 == 0 and row(p) + 128 <= (row(p + 1) if p < 31 else 32 * cs)
+
+    def ok(addrs):
+        return sorted((a % 16) // 2 for a in addrs) == list(range(8))
+
+    for quarter in range(4):
+        pts = list(range(8 * quarter, 8 * quarter + 8))
+        lanes = [(lane >> 2, lane & 3) for lane in pts]
+        for col in range(0, 128, 2):  # epilogue: both 16-byte halves of every double4
+            assert ok([row(p) + col for p in pts]), ("epilogue", quarter, col)
+        for hw in range(4):
+            for half in range(2):
+                for j in range(8):
+                    assert ok([row(8 * hw + g) + 64 * half + 8 * j + 2 * t for g, t in lanes]), ("backward A'", quarter, hw, j)
+        for mi in range(4):
+            for warp in range(8):
+                for e in (0, 2):
+                    a = [row(16 * (mi >> 1) + 2 * g + (mi & 1)) + 4 * (4 * warp + t) + e for g, t in lanes]
+                    assert ok(a), ("delta store", quarter, mi, warp, e)
